@@ -1,0 +1,165 @@
+/*
+ * stgcma.h -- C ABI of libstgcma.so: the B200 (sm_100a) kernels behind the STG-CMA
+ * audio-visual adapter TRAIN STEP (BASELINE.json north_star).
+ *
+ * The reference (kaiw7/STG-CMA) is pure PyTorch and owns no kernels: every entry point
+ * below replaces a group of stock torch call sites inside
+ *     AVE/model/Swin_AVE.py  SwinTransformer2D_Adapter_New.forward(a, v, 'fusion')  :1565-1599
+ * and the autograd graph torch would build for them under the caller's freeze rule
+ * (AVE/traintest_adapt_ave29.py:38-61).  The reference-side binding is the ctypes stub in
+ * INTEGRATION.md; the shipped host side is stg-cma_b200/stgcma/lib.py.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless stated otherwise.
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated or freed
+ *     here; all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit sync.
+ *   - return value: 0 = ok, otherwise an STGCMA_E* code; stgcma_last_error() describes it
+ *     (thread local).  No C++ exception crosses the ABI.
+ *   - `dtype` selects the ACTIVATION storage type: STGCMA_F32 is the fp32 check mode (all math
+ *     fp32 on CUDA cores), STGCMA_BF16 the production mode (bf16 storage, fp32 accumulate,
+ *     tensor cores).  Frozen parameters used by the element-wise kernels (LayerNorm affine,
+ *     bias tables, biases) are always fp32 (the caller's master weights); GEMM weight operands
+ *     use the activation dtype.
+ *   - activations are token-major [rows, channels]; "rows" of the two modalities are stacked
+ *     video first, audio second, because both streams share the frozen weights.
+ *   - refuses to run (STGCMA_EARCH) on anything that is not compute capability 10.x.
+ */
+#ifndef STGCMA_H_
+#define STGCMA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { STGCMA_F32 = 0, STGCMA_BF16 = 1 };
+
+enum {
+  STGCMA_OK = 0,
+  STGCMA_EINVAL = 1,   /* bad argument (shape / alignment / unsupported size) */
+  STGCMA_ECUDA = 2,    /* a CUDA runtime / driver call failed                 */
+  STGCMA_EARCH = 3     /* device is not sm_100                                */
+};
+
+/* GEMM epilogues: v = rowscale[m] * (acc + bias[n])   (rowscale optional, fp32 [M])       */
+enum {
+  STGCMA_EPI_LINEAR = 0,  /* out = res1 + res2 + v                 (each term optional)      */
+  STGCMA_EPI_GELU = 1,    /* out = gelu_erf(v); out_pre = v when out_pre != NULL            */
+  STGCMA_EPI_DGELU = 2,   /* out = v * gelu_erf'(aux[m,n])   (backward through nn.GELU)      */
+  STGCMA_EPI_MULAUX = 3   /* out = v * aux[m,n]              (dropout keep-mask)             */
+};
+
+const char* stgcma_last_error(void);
+int stgcma_version(void);
+/* 0 when device `dev` can run the library (compute capability 10.x), STGCMA_EARCH otherwise */
+int stgcma_check_device(int dev);
+
+/* ---- PatchEmbed3D: Conv3d(k=s=(1,4,4)) + bias + LayerNorm   (Swin_AVE.py:1104-1124) -------
+ * img fp32 [B, Cin, T, H, W] (audio: Cin = 1); w fp32 [C, Cin*16] (= proj.weight flattened),
+ * bias/gamma/beta fp32 [C]; out [B*T, (H/4)*(W/4), C] in `dtype`, token order (b t)(y x).    */
+int stgcma_patch_embed_fwd(const float* img, const float* w, const float* bias, const float* gamma,
+                           const float* beta, void* out, int B, int Cin, int T, int H, int W, int C,
+                           int dtype, void* stream);
+
+/* ---- nn.LayerNorm(C), eps 1e-5, frozen affine (norm1/norm2/norm; Swin_AVE.py:346,353,1314) --
+ * merge = 0: x, y are [rows, C].
+ * merge = 1: PatchMerging gather fused in (Swin_AVE.py:969-978): x is [frames, R, R, C/4],
+ *            y is [frames*(R/2)^2, C] with channel blocks (2y,2x),(2y+1,2x),(2y,2x+1),(2y+1,2x+1);
+ *            rows = frames*(R/2)^2.
+ * mean / rstd fp32 [rows] are written when non-NULL (saved for backward).                    */
+int stgcma_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                         float* rstd, int64_t rows, int C, int merge, int R, int dtype, void* stream);
+/* dx = dres + dLN/dx (dy)   -- no dgamma/dbeta: every LayerNorm on this path is frozen.
+ * merge = 1 scatters back to [frames, R, R, C/4] (dres must then be NULL).                   */
+int stgcma_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                         const float* gamma, const void* dres, void* dx, int64_t rows, int C, int merge,
+                         int R, int dtype, void* stream);
+
+/* ---- nn.Linear family: out[m, n] = epilogue( sum_k A[m,k] * W[g][n,k] + bias[g][n] ) --------
+ * Replaces attn.qkv / attn.proj / mlp.fc1 / mlp.fc2 / downsample.reduction / adapter D_fc1,
+ * D_fc2 / mlp_head (Swin_AVE.py:203,205,116,118,957,15-16,1320-1322) and, with the transposed
+ * weight, their dX backward.  A [M, K] (row stride lda), W [groups, N, K] (row stride ldw,
+ * group stride N*ldw), bias fp32 [groups, N] or NULL.  Rows are split in `groups` equal parts of
+ * M/groups rows, part g using W[g] (groups = 2: per-modality adapter weights).
+ * bf16 mode: tcgen05/TMEM kernel fed by TMA; needs K, lda, ldw multiples of 8 and 16-byte
+ * aligned A / W; N multiple of 8.  res1/res2/aux/out/out_pre share row stride ldo.           */
+int stgcma_gemm(const void* A, const void* W, const float* bias, const void* res1, const void* res2,
+                const float* rowscale, const void* aux, void* out, void* out_pre, int64_t M, int N, int K,
+                int64_t lda, int64_t ldw, int64_t ldo, int groups, int epilogue, int dtype, void* stream);
+
+/* ---- weight gradients of the trainable nn.Linear layers (adapters, head) -------------------
+ * dW[i, j] += sum_m rowscale[m] * A[m, i] * B[m, j]   (i < Ka, j < Nb; dW fp32, row stride ldo)
+ * csumA[i] += sum_m rowscale[m] * A[m, i]  (when non-NULL);  csumB likewise.  Accumulates
+ * (atomics) so the destination is normally a slice of the pre-zeroed flat gradient bucket.   */
+int stgcma_gemm_tn(const void* A, const void* B, const float* rowscale, float* dW, float* csumA,
+                   float* csumB, int64_t M, int Ka, int Nb, int64_t lda, int64_t ldb, int64_t ldo, int dtype,
+                   void* stream);
+
+/* ---- Swin window attention (WindowAttention.forward, temporal=False; Swin_AVE.py:238-276) ---
+ * with torch.roll(-shift) + window_partition + window_reverse + roll(+shift) folded into the
+ * addressing (Swin_AVE.py:728-740,766-776) and the 0/-100 shift mask (:368-387) computed from
+ * coordinates.  qkv [frames, R*R, 3C] channel order [q|k|v] x heads x 32; rpb fp32
+ * [(2ws-1)^2, heads]; out [frames, R*R, C].  head_dim must be 32 (true for every Swin).      */
+int stgcma_window_attn_fwd(const void* qkv, const float* rpb, void* out, int64_t frames, int R, int ws,
+                           int shift, int heads, int dtype, void* stream);
+int stgcma_window_attn_bwd(const void* qkv, const float* rpb, const void* dout, void* dqkv, int64_t frames,
+                           int R, int ws, int shift, int heads, int dtype, void* stream);
+
+/* ---- temporal attention (WindowAttention.forward, temporal=True; Swin_AVE.py:244-255) -------
+ * sequence = the T frames of one (modality, clip, token); qkv [G*B*T, L, 3C]; tbl fp32
+ * [G, 2T-1, heads] (G = 2: video table, audio table); out [G*B*T, L, C].  T <= 16.
+ * bwd accumulates dtbl fp32 [G, 2T-1, heads] (the tables are trainable).                     */
+int stgcma_temporal_attn_fwd(const void* qkv, const float* tbl, void* out, int G, int B, int T, int L,
+                             int heads, int dtype, void* stream);
+int stgcma_temporal_attn_bwd(const void* qkv, const float* tbl, const void* dout, void* dqkv, float* dtbl,
+                             int G, int B, int T, int L, int heads, int dtype, void* stream);
+
+/* ---- cross-modal token attention of the adapters (Swin_AVE.py:753-760 and :801-808) ---------
+ * h [2, frames, L, rp]: GELU(D_fc1(.)) features, video block then audio block, rp = hidden
+ * width padded to a multiple of 16 (pad columns zero).  For each frame and token group
+ *     hv' = hv + gate[0] * softmax(hv ha^T) ha        attn_out[0] = softmax(hv ha^T) ha
+ *     ha' = ha + gate[1] * softmax(ha hv^T) hv        attn_out[1] = softmax(ha hv^T) hv
+ * (logits unscaled, both directions use the un-updated features).
+ *   window variant: groups = the (shifted) ws x ws windows of the R x R token map, L = R*R.
+ *   global variant: one group = all L tokens of the frame (flash-style, never materialises
+ *                   the L x L scores); also writes lse fp32 [2, frames, L].
+ * gate: fp32 [2] on the device.  out, attn_out: [2, frames, L, rp].
+ * bwd: dout = grad wrt h'.  Writes dhpre = (grad wrt h) * gelu'(hpre) when hpre != NULL, else
+ * grad wrt h; accumulates dgate fp32 [2].  The global variant needs `work`: fp32 [2, frames, L]
+ * scratch owned by the caller.                                                                */
+int stgcma_xmodal_window_fwd(const void* h, const float* gate, void* out, void* attn_out, int64_t frames,
+                             int R, int ws, int shift, int rp, int dtype, void* stream);
+int stgcma_xmodal_window_bwd(const void* h, const void* hpre, const float* gate, const void* attn_out,
+                             const void* dout, void* dh, float* dgate, int64_t frames, int R, int ws,
+                             int shift, int rp, int dtype, void* stream);
+int stgcma_xmodal_global_fwd(const void* h, const float* gate, void* out, void* attn_out, float* lse,
+                             int64_t frames, int L, int rp, int dtype, void* stream);
+int stgcma_xmodal_global_bwd(const void* h, const void* hpre, const float* gate, const void* attn_out,
+                             const float* lse, const void* dout, void* dh, float* dgate, float* work,
+                             int64_t frames, int L, int rp, int dtype, void* stream);
+
+/* ---- head pooling: mean over the N tokens of a frame, cat(audio, video) (Swin_AVE.py:1588-1596)
+ * xn [2, frames, N, C] (video, audio) -> feat [frames, 2C] = [audio mean | video mean].      */
+int stgcma_head_pool_fwd(const void* xn, void* feat, int64_t frames, int N, int C, int dtype, void* stream);
+int stgcma_head_pool_bwd(const void* dfeat, void* dxn, int64_t frames, int N, int C, int dtype, void* stream);
+
+/* ---- per-step refresh of the compute copies of the TRAINABLE parameters ---------------------
+ * The optimizer updates the caller's fp32 master nn.Parameters in place; the kernels consume
+ * padded / transposed copies in the activation dtype.  One launch executes a device-resident
+ * table of 2-D copies: dst[c*dst_ld + r] (transpose) or dst[r*dst_ld + c] = src[r*src_ld + c].
+ * Padding regions of dst are never written (they stay zero).                                 */
+typedef struct StgcmaPackEntry {
+  const float* src;
+  void* dst;
+  int32_t rows, cols;       /* of src */
+  int64_t src_ld, dst_ld;   /* in elements */
+  int32_t transpose;
+  int32_t dst_f32;          /* 1: dst is fp32 regardless of dtype (biases, tables) */
+} StgcmaPackEntry;
+int stgcma_pack_params(const StgcmaPackEntry* table_dev, int n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STGCMA_H_ */

@@ -1,0 +1,357 @@
+// Memory-bound kernels of the Swin AVE adapter train step: patch embed (+LayerNorm),
+// LayerNorm forward / frozen-affine backward (optionally fused with the PatchMerging 2x2
+// gather / scatter), head mean-pool + cat.  All 128-bit vectorised, fp32 math.
+#include "common.cuh"
+
+namespace stgcma {
+
+// =========================================================================================
+// LayerNorm: one warp per row.
+// =========================================================================================
+template <typename T, bool MERGE>
+struct RowAddr {
+  // element offset of channel c of logical row `row`
+  int64_t base[4];
+  int C4;
+  __device__ __forceinline__ RowAddr(int64_t row, int C, int R) {
+    if (MERGE) {
+      C4 = C >> 2;
+      const int Rh = R >> 1;
+      const int64_t f = row / (Rh * Rh);
+      const int rem = (int)(row - f * Rh * Rh);
+      const int yy = rem / Rh, xx = rem - yy * Rh;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int dy = q & 1, dx = q >> 1;  // cat order x0,x1,x2,x3 = (0,0),(1,0),(0,1),(1,1)  Swin_AVE.py:971-975
+        base[q] = ((f * R + (2 * yy + dy)) * R + (2 * xx + dx)) * (int64_t)C4;
+      }
+    } else {
+      C4 = C;
+      base[0] = row * (int64_t)C;
+    }
+  }
+  __device__ __forceinline__ int64_t at(int c) const {
+    if (MERGE) {
+      const int q = c / C4;
+      return base[q] + (c - q * C4);
+    }
+    return base[0] + c;
+  }
+};
+
+template <typename T, bool MERGE>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     int64_t rows, int C, int R) {
+  constexpr int V = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RowAddr<T, MERGE> addr(row, C, R);
+  float s = 0.f;
+  for (int c = lane * V; c < C; c += 32 * V) {
+    Vec<T> t;
+    t.load(x + addr.at(c));
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += t.v[i];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane * V; c < C; c += 32 * V) {
+    Vec<T> t;
+    t.load(x + addr.at(c));
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float d = t.v[i] - mean;
+      q += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+  T* yrow = y + row * (int64_t)C;
+  for (int c = lane * V; c < C; c += 32 * V) {
+    Vec<T> t;
+    t.load(x + addr.at(c));
+#pragma unroll
+    for (int i = 0; i < V; ++i) t.v[i] = (t.v[i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i);
+    t.store(yrow + c);
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+template <typename T, bool MERGE>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                     const float* __restrict__ gamma, const T* dres,
+                                                     T* dx, int64_t rows, int C, int R) {  // dres may alias dx
+  constexpr int V = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RowAddr<T, MERGE> addr(row, C, R);
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  const T* dyrow = dy + row * (int64_t)C;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane * V; c < C; c += 32 * V) {
+    Vec<T> g, t;
+    g.load(dyrow + c);
+    t.load(x + addr.at(c));
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float gg = g.v[i] * __ldg(gamma + c + i);
+      s1 += gg;
+      s2 += gg * (t.v[i] - mean) * rstd;
+    }
+  }
+  s1 = warp_sum(s1) / (float)C;
+  s2 = warp_sum(s2) / (float)C;
+  for (int c = lane * V; c < C; c += 32 * V) {
+    Vec<T> g, t, o;
+    g.load(dyrow + c);
+    const int64_t off = addr.at(c);
+    t.load(x + off);
+    if (dres) o.load(dres + off);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float gg = g.v[i] * __ldg(gamma + c + i);
+      const float xh = (t.v[i] - mean) * rstd;
+      const float d = rstd * (gg - s1 - xh * s2);
+      o.v[i] = dres ? o.v[i] + d : d;
+    }
+    o.store(dx + off);
+  }
+}
+
+template <typename T>
+static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                         int64_t rows, int C, int merge, int R, cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div(rows, wpb)), block(wpb * 32);
+  if (merge)
+    ln_fwd_kernel<T, true><<<grid, block, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, C, R);
+  else
+    ln_fwd_kernel<T, false><<<grid, block, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, C, R);
+  return check_launch("layernorm_fwd");
+}
+
+template <typename T>
+static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                         const void* dres, void* dx, int64_t rows, int C, int merge, int R, cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div(rows, wpb)), block(wpb * 32);
+  if (merge)
+    ln_bwd_kernel<T, true><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres,
+                                                   (T*)dx, rows, C, R);
+  else
+    ln_bwd_kernel<T, false><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres,
+                                                    (T*)dx, rows, C, R);
+  return check_launch("layernorm_bwd");
+}
+
+// =========================================================================================
+// Patch embed: Conv3d k=s=(1,4,4) == per-token Linear(Cin*16 -> C), + bias + LayerNorm(C).
+// One block streams (frame, patch-row) strips: the 4 x W x Cin input strip is staged in smem
+// with coalesced loads, the [Cin*16, C] transposed weight stays resident in smem, each warp
+// produces whole tokens (lane = channel mod 32) so the LayerNorm is a warp reduction.
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, T* __restrict__ out, int B,
+                                                          int Cin, int Tn, int H, int W, int C) {
+  extern __shared__ float smem[];
+  const int K = Cin * 16;
+  float* wt = smem;                 // [K][C]
+  float* sb = wt + K * C;           // bias, gamma, beta: [3][C]
+  float* sin = sb + 3 * C;          // [Cin*4][W]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  for (int i = tid; i < K * C; i += blockDim.x) {
+    const int c = i / K, k = i - c * K;  // w is [C][K]
+    wt[k * C + c] = w[i];
+  }
+  for (int i = tid; i < C; i += blockDim.x) {
+    sb[i] = bias[i];
+    sb[C + i] = gamma[i];
+    sb[2 * C + i] = beta[i];
+  }
+  const int Hp = H >> 2, Wp = W >> 2;
+  const int64_t nstrips = (int64_t)B * Tn * Hp;
+  const int per = C >> 5;  // channels per lane (C % 32 == 0, C <= 256)
+  for (int64_t strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+    const int y = (int)(strip % Hp);
+    const int64_t f = strip / Hp;  // frame index b*T + t
+    const int t = (int)(f % Tn);
+    const int b = (int)(f / Tn);
+    __syncthreads();
+    for (int i = tid; i < Cin * 4 * W; i += blockDim.x) {
+      const int rowi = i / W, xx = i - rowi * W;
+      const int ci = rowi >> 2, ky = rowi & 3;
+      sin[i] = img[((((int64_t)b * Cin + ci) * Tn + t) * H + (4 * y + ky)) * W + xx];
+    }
+    __syncthreads();
+    for (int x = warp; x < Wp; x += nwarp) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = (j < per) ? sb[lane + 32 * j] : 0.f;
+      for (int k = 0; k < K; ++k) {
+        const int ci = k >> 4, ky = (k >> 2) & 3, kx = k & 3;
+        const float xv = sin[(ci * 4 + ky) * W + 4 * x + kx];
+        const float* wr = wt + k * C + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < per) acc[j] = fmaf(xv, wr[32 * j], acc[j]);
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < per) s += acc[j];
+      const float mean = warp_sum(s) / (float)C;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < per) {
+          const float d = acc[j] - mean;
+          q += d * d;
+        }
+      const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+      T* o = out + ((f * Hp + y) * (int64_t)Wp + x) * C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < per) {
+          const int c = lane + 32 * j;
+          st_f(o + c, (acc[j] - mean) * rstd * sb[C + c] + sb[2 * C + c]);
+        }
+    }
+  }
+}
+
+// =========================================================================================
+// Head: mean over the N tokens of each frame, feat = [audio | video].
+// =========================================================================================
+template <typename T>
+__global__ void head_pool_fwd_kernel(const T* __restrict__ xn, T* __restrict__ feat, int64_t frames, int N, int C) {
+  const int64_t f = blockIdx.x;
+  const int m = blockIdx.y;  // 0 video, 1 audio
+  const T* src = xn + ((int64_t)m * frames + f) * N * C;
+  T* dst = feat + f * 2 * (int64_t)C + (m == 1 ? 0 : C);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += ld_f(src + (int64_t)n * C + c);
+    st_f(dst + c, s / (float)N);
+  }
+}
+
+template <typename T>
+__global__ void head_pool_bwd_kernel(const T* __restrict__ dfeat, T* __restrict__ dxn, int64_t frames, int N, int C) {
+  const int64_t f = blockIdx.x;
+  const int m = blockIdx.y;
+  T* dst = dxn + ((int64_t)m * frames + f) * N * C;
+  const T* src = dfeat + f * 2 * (int64_t)C + (m == 1 ? 0 : C);
+  const float inv = 1.f / (float)N;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = ld_f(src + c) * inv;
+    for (int n = 0; n < N; ++n) st_f(dst + (int64_t)n * C + c, g);
+  }
+}
+
+// =========================================================================================
+// Trainable-parameter refresh: a table of small 2-D copies (cast / pad / transpose) in one launch.
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) pack_params_kernel(const StgcmaPackEntry* __restrict__ table) {
+  const StgcmaPackEntry e = table[blockIdx.x];
+  const int64_t n = (int64_t)e.rows * e.cols;
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x) {
+    const int r = (int)(i / e.cols), c = (int)(i - (int64_t)r * e.cols);
+    const float v = e.src[(int64_t)r * e.src_ld + c];
+    const int64_t o = e.transpose ? (int64_t)c * e.dst_ld + r : (int64_t)r * e.dst_ld + c;
+    if (e.dst_f32) reinterpret_cast<float*>(e.dst)[o] = v;
+    else st_f(reinterpret_cast<T*>(e.dst) + o, v);
+  }
+}
+
+}  // namespace stgcma
+
+using namespace stgcma;
+
+extern "C" int stgcma_pack_params(const StgcmaPackEntry* table_dev, int n, int dtype, void* stream) {
+  STG_REQUIRE(n > 0 && table_dev, "pack_params: empty table");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(n, 8);
+  if (dtype == STGCMA_F32) pack_params_kernel<float><<<grid, 256, 0, st>>>(table_dev);
+  else if (dtype == STGCMA_BF16) pack_params_kernel<bf16><<<grid, 256, 0, st>>>(table_dev);
+  else STG_REQUIRE(false, "pack_params: bad dtype %d", dtype);
+  return check_launch("pack_params");
+}
+
+extern "C" int stgcma_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                    float* rstd, int64_t rows, int C, int merge, int R, int dtype, void* stream) {
+  STG_REQUIRE(rows > 0 && C > 0, "layernorm_fwd: empty input");
+  STG_REQUIRE(C % 8 == 0 && (!merge || (C % 32 == 0 && R % 2 == 0)), "layernorm_fwd: C=%d must be a multiple of 8 (32 when merging)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == STGCMA_F32) return ln_fwd_launch<float>(x, gamma, beta, y, mean, rstd, rows, C, merge, R, st);
+  if (dtype == STGCMA_BF16) return ln_fwd_launch<bf16>(x, gamma, beta, y, mean, rstd, rows, C, merge, R, st);
+  STG_REQUIRE(false, "layernorm_fwd: bad dtype %d", dtype);
+}
+
+extern "C" int stgcma_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                                    const float* gamma, const void* dres, void* dx, int64_t rows, int C, int merge,
+                                    int R, int dtype, void* stream) {
+  STG_REQUIRE(rows > 0 && C > 0, "layernorm_bwd: empty input");
+  STG_REQUIRE(C % 8 == 0 && (!merge || (C % 32 == 0 && R % 2 == 0)), "layernorm_bwd: C=%d must be a multiple of 8 (32 when merging)", C);
+  STG_REQUIRE(!(merge && dres), "layernorm_bwd: dres is not supported together with merge");
+  STG_REQUIRE(mean && rstd, "layernorm_bwd: saved statistics required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == STGCMA_F32) return ln_bwd_launch<float>(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge, R, st);
+  if (dtype == STGCMA_BF16) return ln_bwd_launch<bf16>(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge, R, st);
+  STG_REQUIRE(false, "layernorm_bwd: bad dtype %d", dtype);
+}
+
+extern "C" int stgcma_patch_embed_fwd(const float* img, const float* w, const float* bias, const float* gamma,
+                                      const float* beta, void* out, int B, int Cin, int T, int H, int W, int C,
+                                      int dtype, void* stream) {
+  STG_REQUIRE(B > 0 && T > 0, "patch_embed_fwd: empty batch");
+  STG_REQUIRE(H % 4 == 0 && W % 4 == 0, "patch_embed_fwd: H, W must be multiples of the 4x4 patch");
+  STG_REQUIRE(C % 32 == 0 && C <= 256, "patch_embed_fwd: C=%d must be a multiple of 32 and <= 256", C);
+  STG_REQUIRE(Cin >= 1 && Cin <= 4, "patch_embed_fwd: Cin=%d unsupported", Cin);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = sizeof(float) * ((size_t)Cin * 16 * C + 3 * C + (size_t)Cin * 4 * W);
+  const int64_t strips = (int64_t)B * T * (H / 4);
+  const int grid = (int)(strips < (int64_t)sm_count() * 4 ? strips : (int64_t)sm_count() * 4);
+  cudaError_t e;
+  if (dtype == STGCMA_F32) {
+    e = cudaFuncSetAttribute(patch_embed_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("patch_embed_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
+    patch_embed_kernel<float><<<grid, 256, smem, st>>>(img, w, bias, gamma, beta, (float*)out, B, Cin, T, H, W, C);
+  } else if (dtype == STGCMA_BF16) {
+    e = cudaFuncSetAttribute(patch_embed_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("patch_embed_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
+    patch_embed_kernel<bf16><<<grid, 256, smem, st>>>(img, w, bias, gamma, beta, (bf16*)out, B, Cin, T, H, W, C);
+  } else {
+    STG_REQUIRE(false, "patch_embed_fwd: bad dtype %d", dtype);
+  }
+  return check_launch("patch_embed_fwd");
+}
+
+extern "C" int stgcma_head_pool_fwd(const void* xn, void* feat, int64_t frames, int N, int C, int dtype, void* stream) {
+  STG_REQUIRE(frames > 0 && N > 0 && C > 0, "head_pool_fwd: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)frames, 2);
+  if (dtype == STGCMA_F32) head_pool_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)xn, (float*)feat, frames, N, C);
+  else if (dtype == STGCMA_BF16) head_pool_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)xn, (bf16*)feat, frames, N, C);
+  else STG_REQUIRE(false, "head_pool_fwd: bad dtype %d", dtype);
+  return check_launch("head_pool_fwd");
+}
+
+extern "C" int stgcma_head_pool_bwd(const void* dfeat, void* dxn, int64_t frames, int N, int C, int dtype, void* stream) {
+  STG_REQUIRE(frames > 0 && N > 0 && C > 0, "head_pool_bwd: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)frames, 2);
+  if (dtype == STGCMA_F32) head_pool_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dfeat, (float*)dxn, frames, N, C);
+  else if (dtype == STGCMA_BF16) head_pool_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dfeat, (bf16*)dxn, frames, N, C);
+  else STG_REQUIRE(false, "head_pool_bwd: bad dtype %d", dtype);
+  return check_launch("head_pool_bwd");
+}

@@ -1,0 +1,645 @@
+// nn.Linear family for the STG-CMA adapter train step.
+//
+//   stgcma_gemm      out = epilogue(A . W^T + bias)
+//       bf16: persistent warp-specialised tcgen05 kernel -- TMA (SWIZZLE_128B, 3-D maps so the
+//             per-modality "groups" never bleed into each other) -> 128 x BN x 64 smem stages ->
+//             tcgen05.mma (cta_group::1, M=128, fp32 accumulators double-buffered in TMEM) ->
+//             4 epilogue warps: tcgen05.ld -> bias -> smem transpose -> coalesced 128-bit
+//             residual / GELU / dGELU epilogue.
+//       fp32: plain CUDA-core tiled GEMM (the check mode; also the numerics reference).
+//   stgcma_gemm_tn   dW += A^T . B   (trainable adapter / head weights), split over rows,
+//                    fp32 atomics into the gradient bucket.
+#include <cuda.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace stgcma {
+
+// =========================================================================================
+// Epilogue (shared)
+// =========================================================================================
+template <typename T>
+__device__ __forceinline__ void epi_elem(const EpiParams& p, int64_t row, int col, float v) {
+  const int64_t off = row * p.ldo + col;
+  T* out = reinterpret_cast<T*>(p.out);
+  if (p.rowscale) v *= p.rowscale[row];
+  switch (p.mode) {
+    case STGCMA_EPI_LINEAR: {
+      if (p.res1) v += ld_f(reinterpret_cast<const T*>(p.res1) + off);
+      if (p.res2) v += ld_f(reinterpret_cast<const T*>(p.res2) + off);
+      st_f(out + off, v);
+    } break;
+    case STGCMA_EPI_GELU: {
+      if (p.out_pre) st_f(reinterpret_cast<T*>(p.out_pre) + off, v);
+      st_f(out + off, gelu_erf(v));
+    } break;
+    case STGCMA_EPI_DGELU: {
+      const float a = ld_f(reinterpret_cast<const T*>(p.aux) + off);
+      st_f(out + off, v * gelu_erf_grad(a));
+    } break;
+    default: {
+      const float a = ld_f(reinterpret_cast<const T*>(p.aux) + off);
+      st_f(out + off, v * a);
+    } break;
+  }
+}
+
+// 8 consecutive bf16 columns of one row, 128-bit accesses.
+__device__ __forceinline__ void epi_vec8(const EpiParams& p, int64_t row, int col, float (&v)[8]) {
+  const int64_t off = row * p.ldo + col;
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+  Vec<bf16> o;
+  if (p.rowscale) {
+    const float s = p.rowscale[row];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= s;
+  }
+  switch (p.mode) {
+    case STGCMA_EPI_LINEAR: {
+      if (p.res1) {
+        Vec<bf16> r;
+        r.load(reinterpret_cast<const bf16*>(p.res1) + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r.v[i];
+      }
+      if (p.res2) {
+        Vec<bf16> r;
+        r.load(reinterpret_cast<const bf16*>(p.res2) + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r.v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = v[i];
+    } break;
+    case STGCMA_EPI_GELU: {
+      if (p.out_pre) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = v[i];
+        o.store(reinterpret_cast<bf16*>(p.out_pre) + off);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = gelu_erf(v[i]);
+    } break;
+    case STGCMA_EPI_DGELU: {
+      Vec<bf16> a;
+      a.load(reinterpret_cast<const bf16*>(p.aux) + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = v[i] * gelu_erf_grad(a.v[i]);
+    } break;
+    default: {
+      Vec<bf16> a;
+      a.load(reinterpret_cast<const bf16*>(p.aux) + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = v[i] * a.v[i];
+    } break;
+  }
+  o.store(out + off);
+}
+
+// =========================================================================================
+// CUDA-core GEMM (fp32 check mode; generic T)
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ W, int64_t group_rows,
+                                                        int N, int K, int64_t lda, int64_t ldw, EpiParams ep) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int g = blockIdx.z;
+  const T* Ag = A + (int64_t)g * group_rows * lda;
+  const T* Wg = W + (int64_t)g * N * ldw;
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + lk + i;
+      const int64_t m = m0 + lr;
+      As[lk + i][lr] = (m < group_rows && k < K) ? ld_f(Ag + m * lda + k) : 0.f;
+      const int n = n0 + lr;
+      Ws[lk + i][lr] = (n < N && k < K) ? ld_f(Wg + (int64_t)n * ldw + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= group_rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const float v = acc[i][j] + (ep.bias ? ep.bias[(int64_t)g * N + n] : 0.f);
+      epi_elem<T>(ep, (int64_t)g * group_rows + m, n, v);
+    }
+  }
+}
+
+// =========================================================================================
+// tcgen05 / TMEM / TMA GEMM (bf16 in, fp32 accumulate)
+// =========================================================================================
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kStageRowF = 36;           // staging row stride in floats (32 + 4 pad, keeps 16 B alignment)
+constexpr int kStagingBytes = 4 * 32 * kStageRowF * 4;
+constexpr int kABytes = BM * BK * 2;     // 16 KiB
+
+struct Params {
+  int64_t group_rows;
+  int N, K, groups;
+  int BN, n_tiles, m_tiles_g, num_tiles, k_blocks, stages;
+  uint32_t tmem_cols;
+  EpiParams epi;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Spin on the phase parity.  A pipeline bug must not hang the GPU: after ~4e9 cycles trap.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0x3ff) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        printf("stgcma gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address  [0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = kABytes + (uint32_t)p.BN * 128u;
+  float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + kStagingBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* tfull = bars + 2 * p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(tfull + s), 1);
+      mbar_init(smem_u32(tempty + s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const int g = mt / p.m_tiles_g;
+        const int m_blk = mt - g * p.m_tiles_g;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(smem_u32(empty + stage), phase ^ 1u);
+          const uint32_t fb = smem_u32(full + stage);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          tma_load_3d(sa, &tmA, fb, kb * BK, m_blk * BM, g);
+          tma_load_3d(sa + kABytes, &tmW, fb, kb * BK, n_blk * p.BN, g);
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tempty + acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(smem_u32(full + stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_sdesc(sa);
+          const uint64_t bdesc = make_sdesc(sa + kABytes);
+          int ksteps = (p.K - kb * BK + 15) >> 4;
+          if (ksteps > BK / 16) ksteps = BK / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in 16 B units
+            mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          mma_commit(smem_u32(empty + stage));
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(smem_u32(tfull + acc));
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> regs -> smem -> global) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* stg = staging + (size_t)(warp - 2) * 32 * kStageRowF;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int g = mt / p.m_tiles_g;
+      const int m_blk = mt - g * p.m_tiles_g;
+      mbar_wait(smem_u32(tfull + acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * (uint32_t)p.BN + ((uint32_t)(q * 32) << 16);
+      const int64_t row_base = (int64_t)m_blk * BM + q * 32;  // first row (within the group) of this warp
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int wc = (p.BN - c0 >= 32) ? 32 : 16;
+        float v[32];
+        if (wc == 32) tmem_ld32(t_row + (uint32_t)c0, v);
+        else tmem_ld16(t_row + (uint32_t)c0, v);
+        if (c0 + wc >= p.BN) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(tempty + acc));
+        }
+        const int ncol0 = n_blk * p.BN + c0;
+        if (p.epi.bias) {
+          const float* b = p.epi.bias + (int64_t)g * p.N + ncol0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < wc && ncol0 + j < p.N) v[j] += __ldg(b + j);
+        }
+        float4* srow = reinterpret_cast<float4*>(stg + lane * kStageRowF);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j * 4 < wc) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int lpr = wc >> 3;            // lanes per row (8 columns each)
+        const int rpp = 32 / lpr;           // rows per pass
+        const int r_in = lane / lpr, seg = lane - r_in * lpr;
+        for (int r0 = 0; r0 < 32; r0 += rpp) {
+          const int rl = r0 + r_in;
+          const int64_t row = row_base + rl;
+          const int col = ncol0 + seg * 8;
+          if (row < p.group_rows && col < p.N) {
+            const float4* s4 = reinterpret_cast<const float4*>(stg + rl * kStageRowF + seg * 8);
+            const float4 a = s4[0], b = s4[1];
+            float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            epi_vec8(p.epi, (int64_t)g * p.group_rows + row, col, o);
+          }
+        }
+        __syncwarp();
+      }
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// bf16 [groups, rows, K] with row stride ld (elements); box = 64 x box_rows x 1, SWIZZLE_128B
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int64_t ld, int groups, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("gemm: cuTensorMapEncodeTiled is not available from the driver");
+    return STGCMA_ECUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d ld=%lld groups=%d box_rows=%d", (int)r,
+              (long long)rows, K, (long long)ld, groups, box_rows);
+    return STGCMA_ECUDA;
+  }
+  return STGCMA_OK;
+}
+
+static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t lda, int64_t ldw, int groups,
+                  const EpiParams& ep, cudaStream_t st) {
+  Params p;
+  p.group_rows = M / groups;
+  p.N = N;
+  p.K = K;
+  p.groups = groups;
+  const int nt = (int)ceil_div(N, 256);
+  p.BN = (int)ceil_div(ceil_div(N, nt), 16) * 16;
+  p.n_tiles = (int)ceil_div(N, p.BN);
+  p.m_tiles_g = (int)ceil_div(p.group_rows, BM);
+  const int64_t tiles = (int64_t)groups * p.m_tiles_g * p.n_tiles;
+  STG_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
+  p.num_tiles = (int)tiles;
+  p.k_blocks = (int)ceil_div(K, BK);
+  const int stage_bytes = kABytes + p.BN * 128;
+  const int budget = 232448 - 1024 - kStagingBytes - 256;
+  int stages = budget / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * p.BN)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.epi = ep;
+
+  CUtensorMap tmA, tmW;
+  int rc = make_map(&tmA, A, p.group_rows, K, lda, groups, BM);
+  if (rc) return rc;
+  rc = make_map(&tmW, W, N, K, ldw, groups, p.BN);
+  if (rc) return rc;
+
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("gemm: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
+    return STGCMA_ECUDA;
+  }
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, p);
+  return check_launch("gemm(tcgen05)");
+}
+
+}  // namespace tc
+
+// =========================================================================================
+// dW += A^T B  (CUDA-core version; generic T)
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_tn_simt_kernel(const T* __restrict__ A, const T* __restrict__ B,
+                                                           const float* __restrict__ rowscale, float* __restrict__ dW,
+                                                           float* __restrict__ csumA, float* __restrict__ csumB, int64_t M,
+                                                           int Ka, int Nb, int64_t lda, int64_t ldb, int64_t ldo,
+                                                           int64_t rows_per_split) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  const int64_t mbeg = (int64_t)blockIdx.z * rows_per_split;
+  int64_t mend = mbeg + rows_per_split;
+  if (mend > M) mend = M;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;  // load: 16 rows x 64 cols, 4 consecutive cols per thread
+  float acc[4][4] = {};
+  float sa[4] = {}, sb[4] = {};
+  for (int64_t m0 = mbeg; m0 < mend; m0 += 16) {
+    const int64_t m = m0 + lr;
+    const float rs = (m < mend && rowscale) ? rowscale[m] : 1.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = i0 + lc + c, j = j0 + lc + c;
+      As[lr][lc + c] = (m < mend && i < Ka) ? ld_f(A + m * lda + i) * rs : 0.f;
+      Bs[lr][lc + c] = (m < mend && j < Nb) ? ld_f(B + m * ldb + j) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sa[i] += a[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (csumB) {
+        const float rk = (rowscale && m0 + k < mend) ? rowscale[m0 + k] : 1.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sb[j] += b[j] * rk;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ii = i0 + ty * 4 + i;
+    if (ii >= Ka) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int jj = j0 + tx * 4 + j;
+      if (jj < Nb) atomicAdd(dW + (int64_t)ii * ldo + jj, acc[i][j]);
+    }
+    if (csumA && blockIdx.y == 0 && tx == 0) atomicAdd(csumA + ii, sa[i]);
+  }
+  if (csumB && blockIdx.x == 0 && ty == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int jj = j0 + tx * 4 + j;
+      if (jj < Nb) atomicAdd(csumB + jj, sb[j]);
+    }
+  }
+}
+
+template <typename T>
+static int gemm_tn_launch(const void* A, const void* B, const float* rowscale, float* dW, float* csumA, float* csumB,
+                          int64_t M, int Ka, int Nb, int64_t lda, int64_t ldb, int64_t ldo, cudaStream_t st) {
+  const int ti = (int)ceil_div(Ka, 64), tj = (int)ceil_div(Nb, 64);
+  int64_t split = ceil_div((int64_t)4 * sm_count(), (int64_t)ti * tj);
+  const int64_t max_split = ceil_div(M, 256);
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  if (split > 65535) split = 65535;
+  int64_t rps = ceil_div(M, split);
+  rps = ceil_div(rps, 16) * 16;
+  split = ceil_div(M, rps);
+  dim3 grid(ti, tj, (unsigned)split);
+  gemm_tn_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)A, (const T*)B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb,
+                                               ldo, rps);
+  return check_launch("gemm_tn");
+}
+
+}  // namespace stgcma
+
+using namespace stgcma;
+
+extern "C" int stgcma_gemm(const void* A, const void* W, const float* bias, const void* res1, const void* res2,
+                           const float* rowscale, const void* aux, void* out, void* out_pre, int64_t M, int N, int K,
+                           int64_t lda, int64_t ldw, int64_t ldo, int groups, int epilogue, int dtype, void* stream) {
+  STG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
+  STG_REQUIRE(groups >= 1 && M % groups == 0, "gemm: M=%lld not divisible by groups=%d", (long long)M, groups);
+  STG_REQUIRE(epilogue >= STGCMA_EPI_LINEAR && epilogue <= STGCMA_EPI_MULAUX, "gemm: bad epilogue %d", epilogue);
+  STG_REQUIRE((epilogue != STGCMA_EPI_DGELU && epilogue != STGCMA_EPI_MULAUX) || aux, "gemm: epilogue %d needs aux", epilogue);
+  STG_REQUIRE(A && W && out, "gemm: null operand");
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiParams ep;
+  ep.bias = bias; ep.res1 = res1; ep.res2 = res2; ep.rowscale = rowscale; ep.aux = aux;
+  ep.out = out; ep.out_pre = out_pre; ep.ldo = ldo; ep.mode = epilogue;
+  if (dtype == STGCMA_F32) {
+    const int64_t gr = M / groups;
+    dim3 grid((unsigned)ceil_div(gr, 64), (unsigned)ceil_div(N, 64), groups);
+    gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)A, (const float*)W, gr, N, K, lda, ldw, ep);
+    return check_launch("gemm(fp32)");
+  }
+  STG_REQUIRE(dtype == STGCMA_BF16, "gemm: bad dtype %d", dtype);
+  STG_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm(bf16): K=%d lda=%lld ldw=%lld must be multiples of 8", K,
+              (long long)lda, (long long)ldw);
+  STG_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "gemm(bf16): N=%d ldo=%lld must be multiples of 8", N, (long long)ldo);
+  STG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
+              "gemm(bf16): operands must be 16-byte aligned");
+  return tc::launch(A, W, M, N, K, lda, ldw, groups, ep, st);
+}
+
+extern "C" int stgcma_gemm_tn(const void* A, const void* B, const float* rowscale, float* dW, float* csumA, float* csumB,
+                              int64_t M, int Ka, int Nb, int64_t lda, int64_t ldb, int64_t ldo, int dtype, void* stream) {
+  STG_REQUIRE(M > 0 && Ka > 0 && Nb > 0, "gemm_tn: empty problem");
+  STG_REQUIRE(A && B && dW, "gemm_tn: null operand");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == STGCMA_F32) return gemm_tn_launch<float>(A, B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb, ldo, st);
+  if (dtype == STGCMA_BF16) return gemm_tn_launch<bf16>(A, B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb, ldo, st);
+  STG_REQUIRE(false, "gemm_tn: bad dtype %d", dtype);
+}

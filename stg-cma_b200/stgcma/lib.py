@@ -1,0 +1,207 @@
+"""ctypes binding of libstgcma.so (C ABI: include/stgcma.h).
+
+There is NO fallback: if the shared library is missing, fails to load, or the device is not
+sm_100, every entry point raises.  PyTorch is used only for device memory and streams; the
+arguments that cross the boundary are raw device pointers, sizes and the current CUDA stream.
+"""
+import ctypes
+import os
+import struct
+
+import torch
+
+F32, BF16 = 0, 1
+EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX = 0, 1, 2, 3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstgcma.so")
+
+_vp, _i, _i64, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+
+# name -> argtypes (restype is always int unless noted)
+_SIGNATURES = {
+    "stgcma_check_device": [_i],
+    "stgcma_patch_embed_fwd": [_fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "stgcma_layernorm_fwd": [_vp, _fp, _fp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _vp],
+    "stgcma_layernorm_bwd": [_vp, _vp, _fp, _fp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "stgcma_gemm": [_vp, _vp, _fp, _vp, _vp, _fp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp],
+    "stgcma_gemm_tn": [_vp, _vp, _fp, _fp, _fp, _fp, _i64, _i, _i, _i64, _i64, _i64, _i, _vp],
+    "stgcma_window_attn_fwd": [_vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_window_attn_bwd": [_vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_temporal_attn_fwd": [_vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "stgcma_temporal_attn_bwd": [_vp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp],
+    "stgcma_xmodal_window_fwd": [_vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_xmodal_window_bwd": [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_xmodal_global_fwd": [_vp, _fp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp],
+    "stgcma_xmodal_global_bwd": [_vp, _vp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _vp],
+    "stgcma_head_pool_fwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
+    "stgcma_head_pool_bwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
+    "stgcma_pack_params": [_vp, _i, _i, _vp],
+}
+EXPORTS = ["stgcma_last_error", "stgcma_version"] + list(_SIGNATURES)
+
+_lib = None
+_launches = 0  # number of kernel-launching ABI calls made so far (bench.py reports the per-step delta)
+
+
+class StgcmaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libstgcma.so (once).  Raises StgcmaError when it is absent -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise StgcmaError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C stg-cma_b200/csrc`).  The STG-CMA B200 path has no CPU / eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.stgcma_last_error.restype = ctypes.c_char_p
+    lib.stgcma_last_error.argtypes = []
+    lib.stgcma_version.restype = _i
+    lib.stgcma_version.argtypes = []
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = _i
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def launches():
+    return _launches
+
+
+def dt(t_or_dtype):
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    if d == torch.float32:
+        return F32
+    if d == torch.bfloat16:
+        return BF16
+    raise StgcmaError(f"unsupported activation dtype {d}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    global _launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise StgcmaError(f"{name} failed ({rc}): {lib.stgcma_last_error().decode()}")
+    _launches += 1
+
+
+_checked = set()
+
+
+def check_device(dev_index):
+    if dev_index in _checked:
+        return
+    lib = load()
+    rc = lib.stgcma_check_device(dev_index)
+    if rc != 0:
+        raise StgcmaError(lib.stgcma_last_error().decode())
+    _checked.add(dev_index)
+
+
+def require_device(*tensors):
+    """Inputs must be CUDA tensors on an sm_100 device: there is no CPU / eager fallback."""
+    for t in tensors:
+        if not t.is_cuda:
+            raise StgcmaError("STG-CMA B200 path needs CUDA tensors: there is no CPU fallback")
+    dev = tensors[0].device
+    check_device(dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------
+# thin typed wrappers (shapes are the caller's responsibility; see include/stgcma.h)
+# ---------------------------------------------------------------------------------------------
+def patch_embed_fwd(img, w, bias, gamma, beta, out, B, Cin, T, H, W, C):
+    _call("stgcma_patch_embed_fwd", _p(img), _p(w), _p(bias), _p(gamma), _p(beta), _p(out), B, Cin, T, H, W, C,
+          dt(out), _stream())
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=0, R=0):
+    _call("stgcma_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, merge, R, dt(x),
+          _stream())
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0):
+    _call("stgcma_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), rows, C, merge, R,
+          dt(x), _stream())
+
+
+def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, aux=None, out_pre=None, lda=None,
+         ldw=None, ldo=None, groups=1, epi=EPI_LINEAR):
+    _call("stgcma_gemm", _p(A), _p(W), _p(bias), _p(res1), _p(res2), _p(rowscale), _p(aux), _p(out), _p(out_pre), M, N,
+          K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A),
+          _stream())
+
+
+def gemm_tn(A, B, dW, M, Ka, Nb, *, lda, ldb, ldo, rowscale=None, csumA=None, csumB=None):
+    _call("stgcma_gemm_tn", _p(A), _p(B), _p(rowscale), _p(dW), _p(csumA), _p(csumB), M, Ka, Nb, lda, ldb, ldo, dt(A),
+          _stream())
+
+
+def window_attn_fwd(qkv, rpb, out, frames, R, ws, shift, heads):
+    _call("stgcma_window_attn_fwd", _p(qkv), _p(rpb), _p(out), frames, R, ws, shift, heads, dt(qkv), _stream())
+
+
+def window_attn_bwd(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads):
+    _call("stgcma_window_attn_bwd", _p(qkv), _p(rpb), _p(dout), _p(dqkv), frames, R, ws, shift, heads, dt(qkv),
+          _stream())
+
+
+def temporal_attn_fwd(qkv, tbl, out, G, B, T, L, heads):
+    _call("stgcma_temporal_attn_fwd", _p(qkv), _p(tbl), _p(out), G, B, T, L, heads, dt(qkv), _stream())
+
+
+def temporal_attn_bwd(qkv, tbl, dout, dqkv, dtbl, G, B, T, L, heads):
+    _call("stgcma_temporal_attn_bwd", _p(qkv), _p(tbl), _p(dout), _p(dqkv), _p(dtbl), G, B, T, L, heads, dt(qkv),
+          _stream())
+
+
+def xmodal_window_fwd(h, gate, out, attn_out, frames, R, ws, shift, rp):
+    _call("stgcma_xmodal_window_fwd", _p(h), _p(gate), _p(out), _p(attn_out), frames, R, ws, shift, rp, dt(h), _stream())
+
+
+def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp):
+    _call("stgcma_xmodal_window_bwd", _p(h), _p(hpre), _p(gate), _p(attn_out), _p(dout), _p(dh), _p(dgate), frames, R,
+          ws, shift, rp, dt(h), _stream())
+
+
+def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp):
+    _call("stgcma_xmodal_global_fwd", _p(h), _p(gate), _p(out), _p(attn_out), _p(lse), frames, L, rp, dt(h), _stream())
+
+
+def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp):
+    _call("stgcma_xmodal_global_bwd", _p(h), _p(hpre), _p(gate), _p(attn_out), _p(lse), _p(dout), _p(dh), _p(dgate),
+          _p(work), frames, L, rp, dt(h), _stream())
+
+
+def head_pool_fwd(xn, feat, frames, N, C):
+    _call("stgcma_head_pool_fwd", _p(xn), _p(feat), frames, N, C, dt(xn), _stream())
+
+
+def head_pool_bwd(dfeat, dxn, frames, N, C):
+    _call("stgcma_head_pool_bwd", _p(dfeat), _p(dxn), frames, N, C, dt(dxn), _stream())
+
+
+PACK_ENTRY = struct.Struct("<QQiiqqii")  # mirrors StgcmaPackEntry (48 bytes)
+
+
+def pack_entry(src, dst, rows, cols, src_ld, dst_ld, transpose, dst_f32):
+    return PACK_ENTRY.pack(src.data_ptr(), dst.data_ptr(), rows, cols, src_ld, dst_ld, int(transpose), int(dst_f32))
+
+
+def pack_params(table_dev, n, dtype_code):
+    _call("stgcma_pack_params", _p(table_dev), n, dtype_code, _stream())

@@ -1,0 +1,316 @@
+"""Per-entry-point torch references for the C ABI in include/stgcma.h (TEST CODE).
+
+Every function has the signature of the matching wrapper in stg-cma_b200/stgcma/lib.py and writes
+its result into the caller's output tensors.  Two uses:
+  * `-m gpu` tests run the CUDA kernel and this reference on the same inputs, op by op;
+  * `-m "not gpu"` tests install these functions in place of the ctypes wrappers
+    (`install_fake_backend`) so the host-side schedule (stgcma/engine.py: buffer wiring, saved
+    tensors, gradient bucket, grouped adapters, drop-path) is checked against the oracle on CPU.
+Backward references are torch autograd of the forward references.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import swin_ave_oracle as O
+
+EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX = 0, 1, 2, 3
+
+
+def _view2d(t, rows, cols, ld):
+    return torch.as_strided(t, (rows, cols), (ld, 1))
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def _dgelu(x):
+    return 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi)
+
+
+def _c(t):  # compute dtype for references
+    return t.to(torch.float64) if t.dtype != torch.float64 else t
+
+
+# ---------------------------------------------------------------------------------------------
+def patch_embed_fwd(img, w, bias, gamma, beta, out, B, Cin, T, H, W, C):
+    x = _c(img).reshape(B, Cin, T, H // 4, 4, W // 4, 4).permute(0, 2, 3, 5, 1, 4, 6).reshape(B * T * (H // 4) * (W // 4), Cin * 16)
+    y = x @ _c(w).t() + _c(bias)
+    y = F.layer_norm(y, (C,), _c(gamma), _c(beta), 1e-5)
+    out.reshape(-1, C).copy_(y)
+
+
+def _merge_index(frames, R, device):
+    """source token (flat over frames*R*R) of each (merged row, quadrant q = dx*2+dy)"""
+    Rh = R // 2
+    f = torch.arange(frames, device=device).view(-1, 1, 1, 1)
+    yy = torch.arange(Rh, device=device).view(1, -1, 1, 1)
+    xx = torch.arange(Rh, device=device).view(1, 1, -1, 1)
+    q = torch.arange(4, device=device).view(1, 1, 1, -1)
+    dy, dx = q % 2, q // 2
+    return ((f * R + 2 * yy + dy) * R + 2 * xx + dx).reshape(-1, 4)
+
+
+def _ln_rows(x, rows, C, merge, R):
+    if merge:
+        C4 = C // 4
+        frames = rows // ((R // 2) ** 2)
+        idx = _merge_index(frames, R, x.device)
+        return x.reshape(-1, C4)[idx.reshape(-1)].reshape(rows, C), idx
+    return x.reshape(-1, C)[:rows], None
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=0, R=0):
+    xr, _ = _ln_rows(_c(x), rows, C, merge, R)
+    mu = xr.mean(-1)
+    var = ((xr - mu[:, None]) ** 2).mean(-1)
+    rs = torch.rsqrt(var + 1e-5)
+    y.reshape(-1, C)[:rows].copy_((xr - mu[:, None]) * rs[:, None] * _c(gamma) + _c(beta))
+    if mean is not None:
+        mean.copy_(mu)
+    if rstd is not None:
+        rstd.copy_(rs)
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0):
+    xr, idx = _ln_rows(_c(x), rows, C, merge, R)
+    g = _c(dy).reshape(-1, C)[:rows] * _c(gamma)
+    xh = (xr - _c(mean)[:, None]) * _c(rstd)[:, None]
+    d = _c(rstd)[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if merge:
+        C4 = C // 4
+        tmp = torch.zeros(dx.numel() // C4, C4, dtype=d.dtype, device=d.device)
+        tmp[idx.reshape(-1)] = d.reshape(-1, C4)
+        dx.reshape(-1, C4).copy_(tmp)
+    else:
+        if dres is not None:
+            d = d + _c(dres).reshape(-1, C)[:rows]
+        dx.reshape(-1, C)[:rows].copy_(d)
+
+
+def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, aux=None, out_pre=None, lda=None,
+         ldw=None, ldo=None, groups=1, epi=EPI_LINEAR):
+    lda = K if lda is None else lda
+    ldw = K if ldw is None else ldw
+    ldo = N if ldo is None else ldo
+    Mg = M // groups
+    a = _c(_view2d(A, M, K, lda)).reshape(groups, Mg, K)
+    w = _c(torch.as_strided(W, (groups, N, K), (N * ldw, ldw, 1)))
+    v = torch.einsum("gmk,gnk->gmn", a, w)
+    if bias is not None:
+        v = v + _c(bias).reshape(groups, 1, N)
+    v = v.reshape(M, N)
+    if rowscale is not None:
+        v = v * _c(rowscale).reshape(M, 1)
+    o = _view2d(out, M, N, ldo)
+    if epi == EPI_LINEAR:
+        if res1 is not None:
+            v = v + _c(_view2d(res1, M, N, ldo))
+        if res2 is not None:
+            v = v + _c(_view2d(res2, M, N, ldo))
+        o.copy_(v)
+    elif epi == EPI_GELU:
+        if out_pre is not None:
+            _view2d(out_pre, M, N, ldo).copy_(v)
+        o.copy_(_gelu(v))
+    elif epi == EPI_DGELU:
+        o.copy_(v * _dgelu(_c(_view2d(aux, M, N, ldo))))
+    else:
+        o.copy_(v * _c(_view2d(aux, M, N, ldo)))
+
+
+def gemm_tn(A, B, dW, M, Ka, Nb, *, lda, ldb, ldo, rowscale=None, csumA=None, csumB=None):
+    a = _c(_view2d(A, M, Ka, lda))
+    b = _c(_view2d(B, M, Nb, ldb))
+    if rowscale is not None:
+        rs = _c(rowscale).reshape(M, 1)
+        a = a * rs
+        bs = b * rs
+    else:
+        bs = b
+    o = _view2d(dW, Ka, Nb, ldo)
+    o.add_((a.t() @ b).to(o.dtype))
+    if csumA is not None:
+        csumA[:Ka].add_(a.sum(0).to(csumA.dtype))
+    if csumB is not None:
+        csumB[:Nb].add_(bs.sum(0).to(csumB.dtype))
+
+
+# ---- attention ------------------------------------------------------------------------------
+def _window_attn(qkv, rpb, frames, R, ws, shift, heads):
+    C3 = qkv.shape[-1]
+    C = C3 // 3
+    L = R * R
+    idx = O.window_token_index(R, ws, shift).to(qkv.device)           # [nW, N]
+    x = qkv.reshape(frames, L, C3)[:, idx]                            # [frames, nW, N, 3C]
+    q, k, v = O._split_heads(x, heads)
+    N = ws * ws
+    s = (q * 32 ** -0.5) @ k.transpose(-1, -2)
+    bias = rpb[O.relative_position_index(ws).reshape(-1).to(qkv.device)].reshape(N, N, heads).permute(2, 0, 1)
+    s = s + bias
+    if shift > 0:
+        s = s + O.shifted_window_mask(R, ws, shift).to(s)[None, :, None]
+    o = O._merge_heads(torch.softmax(s, -1) @ v)                      # [frames, nW, N, C]
+    flat = idx.reshape(-1)
+    inv = torch.empty_like(flat)
+    inv[flat] = torch.arange(flat.numel(), device=flat.device)
+    return o.reshape(frames, L, C)[:, inv]
+
+
+def window_attn_fwd(qkv, rpb, out, frames, R, ws, shift, heads):
+    out.reshape(frames, R * R, -1).copy_(_window_attn(_c(qkv), _c(rpb), frames, R, ws, shift, heads))
+
+
+@torch.enable_grad()
+def window_attn_bwd(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads):
+    q = _c(qkv).detach().clone().requires_grad_(True)
+    o = _window_attn(q, _c(rpb), frames, R, ws, shift, heads)
+    (g,) = torch.autograd.grad(o, q, _c(dout).reshape(o.shape))
+    dqkv.copy_(g.reshape(dqkv.shape))
+
+
+def _temporal_attn(qkv, tbl, G, B, T, L, heads):
+    C3 = qkv.shape[-1]
+    C = C3 // 3
+    x = qkv.reshape(G, B, T, L, C3).permute(0, 1, 3, 2, 4)            # [G, B, L, T, 3C]
+    q, k, v = O._split_heads(x, heads)                                # [G, B, L, h, T, 32]
+    s = (q * 32 ** -0.5) @ k.transpose(-1, -2)
+    rel = O.temporal_relative_coords(T).to(qkv.device)
+    bias = tbl[:, rel].reshape(G, T, T, heads).permute(0, 3, 1, 2)    # [G, h, T, T]
+    s = s + bias[:, None, None]
+    o = O._merge_heads(torch.softmax(s, -1) @ v)                      # [G, B, L, T, C]
+    return o.permute(0, 1, 3, 2, 4).reshape(G * B * T * L, C)
+
+
+def temporal_attn_fwd(qkv, tbl, out, G, B, T, L, heads):
+    out.reshape(G * B * T * L, -1).copy_(_temporal_attn(_c(qkv), _c(tbl), G, B, T, L, heads))
+
+
+@torch.enable_grad()
+def temporal_attn_bwd(qkv, tbl, dout, dqkv, dtbl, G, B, T, L, heads):
+    q = _c(qkv).detach().clone().requires_grad_(True)
+    t = _c(tbl).detach().clone().requires_grad_(True)
+    o = _temporal_attn(q, t, G, B, T, L, heads)
+    gq, gt = torch.autograd.grad(o, (q, t), _c(dout).reshape(o.shape))
+    dqkv.copy_(gq.reshape(dqkv.shape))
+    dtbl.reshape(t.shape).add_(gt.to(dtbl.dtype))
+
+
+def _xmodal(hv, ha, gate):
+    s = hv @ ha.transpose(-1, -2)
+    a2v = torch.softmax(s, -1) @ ha
+    v2a = torch.softmax(s.transpose(-1, -2), -1) @ hv
+    return hv + gate[0] * a2v, ha + gate[1] * v2a, a2v, v2a, torch.logsumexp(s, -1), torch.logsumexp(s.transpose(-1, -2), -1)
+
+
+def _xw(h, gate, frames, R, ws, shift, rp):
+    L = R * R
+    idx = O.window_token_index(R, ws, shift).to(h.device)
+    x = h.reshape(2, frames, L, rp)[:, :, idx]                        # [2, frames, nW, N, rp]
+    ov, oa, a2v, v2a, _, _ = _xmodal(x[0], x[1], gate)
+    flat = idx.reshape(-1)
+    inv = torch.empty_like(flat)
+    inv[flat] = torch.arange(flat.numel(), device=flat.device)
+
+    def back(t):
+        return t.reshape(frames, L, rp)[:, inv]
+    return torch.stack((back(ov), back(oa))), torch.stack((back(a2v), back(v2a)))
+
+
+def xmodal_window_fwd(h, gate, out, attn_out, frames, R, ws, shift, rp):
+    o, a = _xw(_c(h), _c(gate), frames, R, ws, shift, rp)
+    out.copy_(o.reshape(out.shape))
+    attn_out.copy_(a.reshape(attn_out.shape))
+
+
+@torch.enable_grad()
+def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp):
+    hh = _c(h).detach().clone().requires_grad_(True)
+    gg = _c(gate).detach().clone().requires_grad_(True)
+    o, _ = _xw(hh, gg, frames, R, ws, shift, rp)
+    gh, ggate = torch.autograd.grad(o, (hh, gg), _c(dout).reshape(o.shape))
+    if hpre is not None:
+        gh = gh * _dgelu(_c(hpre)).reshape(gh.shape)
+    dh.copy_(gh.reshape(dh.shape))
+    dgate.add_(ggate.to(dgate.dtype))
+
+
+def _xg(h, gate, frames, L, rp):
+    x = h.reshape(2, frames, L, rp)
+    ov, oa, a2v, v2a, lv, la = _xmodal(x[0], x[1], gate)
+    return torch.stack((ov, oa)), torch.stack((a2v, v2a)), torch.stack((lv, la))
+
+
+def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp):
+    o, a, l = _xg(_c(h), _c(gate), frames, L, rp)
+    out.copy_(o.reshape(out.shape))
+    attn_out.copy_(a.reshape(attn_out.shape))
+    lse.copy_(l.reshape(lse.shape))
+
+
+@torch.enable_grad()
+def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp):
+    hh = _c(h).detach().clone().requires_grad_(True)
+    gg = _c(gate).detach().clone().requires_grad_(True)
+    o, _, _ = _xg(hh, gg, frames, L, rp)
+    gh, ggate = torch.autograd.grad(o, (hh, gg), _c(dout).reshape(o.shape))
+    if hpre is not None:
+        gh = gh * _dgelu(_c(hpre)).reshape(gh.shape)
+    dh.copy_(gh.reshape(dh.shape))
+    dgate.add_(ggate.to(dgate.dtype))
+
+
+def head_pool_fwd(xn, feat, frames, N, C):
+    x = _c(xn).reshape(2, frames, N, C).mean(2)
+    feat.copy_(torch.cat((x[1], x[0]), -1))
+
+
+def head_pool_bwd(dfeat, dxn, frames, N, C):
+    d = _c(dfeat).reshape(frames, 2, C) / N                           # [:, 0] audio, [:, 1] video
+    dxn.reshape(2, frames, N, C).copy_(torch.stack((d[:, 1], d[:, 0]))[:, :, None, :].expand(2, frames, N, C))
+
+
+# ---- parameter packing (host memory only: used by the CPU fake backend) ------------------------
+_DT = {0: torch.float32, 1: torch.bfloat16, 2: torch.float64}
+_CT = {torch.float32: ctypes.c_float, torch.float64: ctypes.c_double}
+
+
+def pack_params(table_dev, n, dtype_code):
+    import struct
+    import numpy as np
+    st = struct.Struct("<QQiiqqii")
+    raw = bytes(table_dev.cpu().numpy().tobytes())
+    dst_dtype = _DT[dtype_code]
+    for e in range(n):
+        src, dst, rows, cols, sld, dld, tr, f32 = st.unpack_from(raw, e * st.size)
+        s = np.ctypeslib.as_array(ctypes.cast(src, ctypes.POINTER(ctypes.c_float)), shape=((rows - 1) * sld + cols,))
+        sv = torch.from_numpy(np.lib.stride_tricks.as_strided(s, (rows, cols), (sld * 4, 4)).copy())
+        dt_ = torch.float32 if f32 else dst_dtype
+        if dt_ == torch.bfloat16:
+            raise NotImplementedError("fake backend packs fp32 / fp64 only")
+        ct = _CT[dt_]
+        esz = ctypes.sizeof(ct)
+        if tr:
+            d = np.ctypeslib.as_array(ctypes.cast(dst, ctypes.POINTER(ct)), shape=((cols - 1) * dld + rows,))
+            dv = np.lib.stride_tricks.as_strided(d, (cols, rows), (dld * esz, esz))
+            dv[...] = sv.t().to(dt_).numpy()
+        else:
+            d = np.ctypeslib.as_array(ctypes.cast(dst, ctypes.POINTER(ct)), shape=((rows - 1) * dld + cols,))
+            dv = np.lib.stride_tricks.as_strided(d, (rows, cols), (dld * esz, esz))
+            dv[...] = sv.to(dt_).numpy()
+
+
+def install_fake_backend(monkeypatch, lib_module):
+    """Route every kernel wrapper of stgcma.lib to the torch references above (CPU tests only)."""
+    import sys
+    me = sys.modules[__name__]
+    for name in ("patch_embed_fwd", "layernorm_fwd", "layernorm_bwd", "gemm", "gemm_tn", "window_attn_fwd",
+                 "window_attn_bwd", "temporal_attn_fwd", "temporal_attn_bwd", "xmodal_window_fwd", "xmodal_window_bwd",
+                 "xmodal_global_fwd", "xmodal_global_bwd", "head_pool_fwd", "head_pool_bwd", "pack_params"):
+        monkeypatch.setattr(lib_module, name, getattr(me, name))
+    monkeypatch.setattr(lib_module, "require_device", lambda *t: None)
+    monkeypatch.setattr(lib_module, "dt", lambda d: {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}[
+        d.dtype if isinstance(d, torch.Tensor) else d])
