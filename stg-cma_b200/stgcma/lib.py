@@ -94,7 +94,7 @@ def _stream():
 def _call(name, *args):
     global _launches
     lib = load()
-    rc = getattr(lib, name)(*args)
+    rc = getattr(lib, name)(*args, _stream())  # every kernel entry point takes the stream last
     if rc != 0:
         raise StgcmaError(f"{name} failed ({rc}): {lib.stgcma_last_error().decode()}")
     _launches += 1
@@ -127,73 +127,68 @@ def require_device(*tensors):
 # ---------------------------------------------------------------------------------------------
 def patch_embed_fwd(img, w, bias, gamma, beta, out, B, Cin, T, H, W, C):
     _call("stgcma_patch_embed_fwd", _p(img), _p(w), _p(bias), _p(gamma), _p(beta), _p(out), B, Cin, T, H, W, C,
-          dt(out), _stream())
+          dt(out))
 
 
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=0, R=0):
-    _call("stgcma_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, merge, R, dt(x),
-          _stream())
+    _call("stgcma_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, merge, R, dt(x))
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0):
     _call("stgcma_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), rows, C, merge, R,
-          dt(x), _stream())
+          dt(x))
 
 
 def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, aux=None, out_pre=None, lda=None,
          ldw=None, ldo=None, groups=1, epi=EPI_LINEAR):
     _call("stgcma_gemm", _p(A), _p(W), _p(bias), _p(res1), _p(res2), _p(rowscale), _p(aux), _p(out), _p(out_pre), M, N,
-          K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A),
-          _stream())
+          K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A))
 
 
 def gemm_tn(A, B, dW, M, Ka, Nb, *, lda, ldb, ldo, rowscale=None, csumA=None, csumB=None):
-    _call("stgcma_gemm_tn", _p(A), _p(B), _p(rowscale), _p(dW), _p(csumA), _p(csumB), M, Ka, Nb, lda, ldb, ldo, dt(A),
-          _stream())
+    _call("stgcma_gemm_tn", _p(A), _p(B), _p(rowscale), _p(dW), _p(csumA), _p(csumB), M, Ka, Nb, lda, ldb, ldo, dt(A))
 
 
 def window_attn_fwd(qkv, rpb, out, frames, R, ws, shift, heads):
-    _call("stgcma_window_attn_fwd", _p(qkv), _p(rpb), _p(out), frames, R, ws, shift, heads, dt(qkv), _stream())
+    _call("stgcma_window_attn_fwd", _p(qkv), _p(rpb), _p(out), frames, R, ws, shift, heads, dt(qkv))
 
 
 def window_attn_bwd(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads):
-    _call("stgcma_window_attn_bwd", _p(qkv), _p(rpb), _p(dout), _p(dqkv), frames, R, ws, shift, heads, dt(qkv),
-          _stream())
+    _call("stgcma_window_attn_bwd", _p(qkv), _p(rpb), _p(dout), _p(dqkv), frames, R, ws, shift, heads, dt(qkv))
 
 
 def temporal_attn_fwd(qkv, tbl, out, G, B, T, L, heads):
-    _call("stgcma_temporal_attn_fwd", _p(qkv), _p(tbl), _p(out), G, B, T, L, heads, dt(qkv), _stream())
+    _call("stgcma_temporal_attn_fwd", _p(qkv), _p(tbl), _p(out), G, B, T, L, heads, dt(qkv))
 
 
 def temporal_attn_bwd(qkv, tbl, dout, dqkv, dtbl, G, B, T, L, heads):
-    _call("stgcma_temporal_attn_bwd", _p(qkv), _p(tbl), _p(dout), _p(dqkv), _p(dtbl), G, B, T, L, heads, dt(qkv),
-          _stream())
+    _call("stgcma_temporal_attn_bwd", _p(qkv), _p(tbl), _p(dout), _p(dqkv), _p(dtbl), G, B, T, L, heads, dt(qkv))
 
 
 def xmodal_window_fwd(h, gate, out, attn_out, frames, R, ws, shift, rp):
-    _call("stgcma_xmodal_window_fwd", _p(h), _p(gate), _p(out), _p(attn_out), frames, R, ws, shift, rp, dt(h), _stream())
+    _call("stgcma_xmodal_window_fwd", _p(h), _p(gate), _p(out), _p(attn_out), frames, R, ws, shift, rp, dt(h))
 
 
 def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp):
     _call("stgcma_xmodal_window_bwd", _p(h), _p(hpre), _p(gate), _p(attn_out), _p(dout), _p(dh), _p(dgate), frames, R,
-          ws, shift, rp, dt(h), _stream())
+          ws, shift, rp, dt(h))
 
 
 def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp):
-    _call("stgcma_xmodal_global_fwd", _p(h), _p(gate), _p(out), _p(attn_out), _p(lse), frames, L, rp, dt(h), _stream())
+    _call("stgcma_xmodal_global_fwd", _p(h), _p(gate), _p(out), _p(attn_out), _p(lse), frames, L, rp, dt(h))
 
 
 def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp):
     _call("stgcma_xmodal_global_bwd", _p(h), _p(hpre), _p(gate), _p(attn_out), _p(lse), _p(dout), _p(dh), _p(dgate),
-          _p(work), frames, L, rp, dt(h), _stream())
+          _p(work), frames, L, rp, dt(h))
 
 
 def head_pool_fwd(xn, feat, frames, N, C):
-    _call("stgcma_head_pool_fwd", _p(xn), _p(feat), frames, N, C, dt(xn), _stream())
+    _call("stgcma_head_pool_fwd", _p(xn), _p(feat), frames, N, C, dt(xn))
 
 
 def head_pool_bwd(dfeat, dxn, frames, N, C):
-    _call("stgcma_head_pool_bwd", _p(dfeat), _p(dxn), frames, N, C, dt(dxn), _stream())
+    _call("stgcma_head_pool_bwd", _p(dfeat), _p(dxn), frames, N, C, dt(dxn))
 
 
 PACK_ENTRY = struct.Struct("<QQiiqqii")  # mirrors StgcmaPackEntry (48 bytes)
@@ -204,4 +199,4 @@ def pack_entry(src, dst, rows, cols, src_ld, dst_ld, transpose, dst_f32):
 
 
 def pack_params(table_dev, n, dtype_code):
-    _call("stgcma_pack_params", _p(table_dev), n, dtype_code, _stream())
+    _call("stgcma_pack_params", _p(table_dev), n, dtype_code)

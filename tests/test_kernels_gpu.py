@@ -1,0 +1,309 @@
+"""Per-entry-point parity: each C-ABI kernel of libstgcma.so (called through the ctypes wrappers of
+stgcma/lib.py) against its torch fp64 reference in tests/ref_ops.py on the same seeded inputs.
+
+Tolerances (relative = max|got - ref| / max|ref| per tensor):
+  fp32 check mode  : 1e-4 per kernel (the end-to-end bar from BASELINE.json is 1e-3)
+  bf16 production  : 1e-2 per kernel (end-to-end bar 2e-2); the reference is fed the SAME
+                     bf16-rounded inputs, so this measures the kernel, not the input rounding.
+"""
+import pytest
+import torch
+
+import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+
+
+def L():
+    import stgcma.lib as lib
+    return lib
+
+
+def rel(got, ref):
+    ref = ref.double().cpu()
+    return float((got.double().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def rnd(*shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def cpu(t):
+    return None if t is None else t.detach().cpu()
+
+
+# ---------------------------------------------------------------------------------------------
+GEMM_CASES = [
+    # M, N, K, groups, epi, opts
+    (300, 288, 96, 1, R.EPI_LINEAR, dict(bias=True)),                 # K tail (96 = 64 + 32), M tail, BN = 144
+    (256, 96, 384, 1, R.EPI_LINEAR, dict(bias=True, res1=True)),
+    (1000, 1536, 768, 1, R.EPI_LINEAR, dict(bias=True)),              # several N tiles, 12 k-blocks
+    (260, 16, 96, 2, R.EPI_GELU, dict(bias=True, out_pre=True)),      # adapter fc1: grouped, N = 16
+    (260, 96, 16, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, rowscale=True)),  # adapter fc2: K = 16
+    (384, 384, 96, 1, R.EPI_GELU, dict(bias=True, out_pre=True)),     # mlp.fc1
+    (384, 384, 96, 1, R.EPI_DGELU, dict(aux=True)),
+    (130, 48, 192, 2, R.EPI_DGELU, dict(aux=True, rowscale=True)),
+    (20, 512, 1536, 1, R.EPI_MULAUX, dict(bias=True, aux=True)),      # head, tiny M
+    (20, 32, 512, 1, R.EPI_LINEAR, dict(bias=True)),
+    (640, 768, 3072, 1, R.EPI_LINEAR, dict(bias=True, res1=True)),    # mlp.fc2 at stage 3: 48 k-blocks
+    (50000, 288, 96, 1, R.EPI_LINEAR, dict(bias=True)),               # many tiles per CTA (persistent loop, phases)
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: f"M{c[0]}N{c[1]}K{c[2]}g{c[3]}e{c[4]}")
+def test_gemm(case, dtype):
+    M, N, K, groups, epi, o = case
+    A = rnd(M, K, dtype=dtype, seed=1)
+    W = rnd(groups, N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    bias = rnd(groups, N, dtype=torch.float32, seed=3) if o.get("bias") else None
+    res1 = rnd(M, N, dtype=dtype, seed=4) if o.get("res1") else None
+    res2 = rnd(M, N, dtype=dtype, seed=5) if o.get("res2") else None
+    rowscale = (torch.rand(M, generator=torch.Generator().manual_seed(6)) * 2).cuda() if o.get("rowscale") else None
+    aux = rnd(M, N, dtype=dtype, seed=7) if o.get("aux") else None
+    out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
+    out_pre = torch.full((M, N), float("nan"), dtype=dtype, device="cuda") if o.get("out_pre") else None
+    L().gemm(A, W, out, M, N, K, bias=bias, res1=res1, res2=res2, rowscale=rowscale, aux=aux, out_pre=out_pre,
+             groups=groups, epi=epi)
+    torch.cuda.synchronize()
+    r_out = torch.empty(M, N, dtype=torch.float64)
+    r_pre = torch.empty(M, N, dtype=torch.float64) if out_pre is not None else None
+    R.gemm(cpu(A), cpu(W), r_out, M, N, K, bias=cpu(bias), res1=cpu(res1), res2=cpu(res2), rowscale=cpu(rowscale),
+           aux=cpu(aux), out_pre=r_pre, groups=groups, epi=epi)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, r_out) < TOL[dtype]
+    if out_pre is not None:
+        assert rel(out_pre, r_pre) < TOL[dtype]
+
+
+def test_gemm_bf16_padded_strides():
+    """lda / ldo larger than the logical width (adapter hidden tensors are stored padded)."""
+    M, N, K, lda, ldo = 200, 96, 16, 32, 128
+    dtype = torch.bfloat16
+    A = rnd(M, lda, dtype=dtype, seed=1)
+    W = rnd(N, K, dtype=dtype, seed=2)
+    out = torch.zeros(M, ldo, dtype=dtype, device="cuda")
+    L().gemm(A, W, out, M, N, K, lda=lda, ldo=ldo)
+    torch.cuda.synchronize()
+    ref = cpu(A)[:, :K].double() @ cpu(W).double().t()
+    assert rel(out[:, :N], ref) < 1e-2
+    assert float(out[:, N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,Ka,lda,Nb,ldb,rs", [(5000, 16, 16, 96, 96, False), (333, 96, 96, 12, 16, True),
+                                               (20, 29, 32, 512, 512, False), (70000, 48, 48, 768, 768, False)])
+def test_gemm_tn(M, Ka, lda, Nb, ldb, rs, dtype):
+    A = rnd(M, lda, dtype=dtype, seed=1)
+    B = rnd(M, ldb, dtype=dtype, seed=2)
+    rowscale = (torch.rand(M, generator=torch.Generator().manual_seed(3)) * 2).cuda() if rs else None
+    dW = torch.zeros(Ka, Nb, device="cuda")
+    ca = torch.zeros(Ka, device="cuda")
+    cb = torch.zeros(Nb, device="cuda")
+    L().gemm_tn(A, B, dW, M, Ka, Nb, lda=lda, ldb=ldb, ldo=Nb, rowscale=rowscale, csumA=ca, csumB=cb)
+    torch.cuda.synchronize()
+    r_dW, r_ca, r_cb = torch.zeros(Ka, Nb, dtype=torch.float64), torch.zeros(Ka, dtype=torch.float64), torch.zeros(Nb, dtype=torch.float64)
+    R.gemm_tn(cpu(A), cpu(B), r_dW, M, Ka, Nb, lda=lda, ldb=ldb, ldo=Nb, rowscale=cpu(rowscale), csumA=r_ca, csumB=r_cb)
+    tol = 1e-4  # fp32 accumulation of exactly-represented inputs in both modes
+    assert rel(dW, r_dW) < tol and rel(ca, r_ca) < tol and rel(cb, r_cb) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,C", [(1000, 96), (77, 384), (64, 1536), (9, 3072)])
+def test_layernorm(rows, C, dtype):
+    x = rnd(rows, C, dtype=dtype, seed=1, scale=2.0) + 0.5
+    gamma, beta = rnd(C, dtype=torch.float32, seed=2) + 1.0, rnd(C, dtype=torch.float32, seed=3)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    L().layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C)
+    r_y, r_m, r_r = torch.empty(rows, C, dtype=torch.float64), torch.empty(rows, dtype=torch.float64), torch.empty(rows, dtype=torch.float64)
+    R.layernorm_fwd(cpu(x), cpu(gamma), cpu(beta), r_y, r_m, r_r, rows, C)
+    assert rel(y, r_y) < TOL[dtype] and rel(mean, r_m) < 1e-5 and rel(rstd, r_r) < 1e-5
+    dy, dres = rnd(rows, C, dtype=dtype, seed=4), rnd(rows, C, dtype=dtype, seed=5)
+    dx = torch.empty_like(x)
+    L().layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C)
+    r_dx = torch.empty(rows, C, dtype=torch.float64)
+    R.layernorm_bwd(cpu(dy), cpu(x), r_m, r_r, cpu(gamma), cpu(dres), r_dx, rows, C)
+    assert rel(dx, r_dx) < TOL[dtype]
+    # in-place residual accumulation (dres aliases dx), as the engine uses it
+    dx2 = dres.clone()
+    L().layernorm_bwd(dy, x, mean, rstd, gamma, dx2, dx2, rows, C)
+    assert torch.equal(dx2, dx)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_layernorm_patch_merge(dtype):
+    frames, Rr, C4 = 3, 14, 96
+    C = 4 * C4
+    rows = frames * (Rr // 2) ** 2
+    x = rnd(frames * Rr * Rr, C4, dtype=dtype, seed=1)
+    gamma, beta = rnd(C, dtype=torch.float32, seed=2) + 1.0, rnd(C, dtype=torch.float32, seed=3)
+    y = torch.empty(rows, C, dtype=dtype, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    L().layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=1, R=Rr)
+    r_y, r_m, r_r = torch.empty(rows, C, dtype=torch.float64), torch.empty(rows, dtype=torch.float64), torch.empty(rows, dtype=torch.float64)
+    R.layernorm_fwd(cpu(x), cpu(gamma), cpu(beta), r_y, r_m, r_r, rows, C, merge=1, R=Rr)
+    assert rel(y, r_y) < TOL[dtype]
+    dy = rnd(rows, C, dtype=dtype, seed=4)
+    dx = torch.full_like(x, float("nan"))
+    L().layernorm_bwd(dy, x, mean, rstd, gamma, None, dx, rows, C, merge=1, R=Rr)
+    r_dx = torch.empty(frames * Rr * Rr, C4, dtype=torch.float64)
+    R.layernorm_bwd(cpu(dy), cpu(x), r_m, r_r, cpu(gamma), None, r_dx, rows, C, merge=1, R=Rr)
+    assert rel(dx, r_dx) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("Cin,C", [(3, 96), (1, 128), (3, 192)])
+def test_patch_embed(Cin, C, dtype):
+    B, T, H = 2, 3, 224
+    img = rnd(B, Cin, T, H, H, dtype=torch.float32, seed=1)
+    w, b = rnd(C, Cin * 16, dtype=torch.float32, seed=2, scale=0.1), rnd(C, dtype=torch.float32, seed=3, scale=0.1)
+    gamma, beta = rnd(C, dtype=torch.float32, seed=4) + 1.0, rnd(C, dtype=torch.float32, seed=5)
+    out = torch.full((B * T * 56 * 56, C), float("nan"), dtype=dtype, device="cuda")
+    L().patch_embed_fwd(img, w, b, gamma, beta, out, B, Cin, T, H, H, C)
+    ref = torch.empty(B * T * 56 * 56, C, dtype=torch.float64)
+    R.patch_embed_fwd(cpu(img), cpu(w), cpu(b), cpu(gamma), cpu(beta), ref, B, Cin, T, H, H, C)
+    assert rel(out, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("Rr,ws,shift,heads,frames", [(14, 7, 0, 3, 4), (14, 7, 3, 3, 4), (28, 7, 3, 2, 2), (7, 7, 0, 4, 5)])
+def test_window_attention(Rr, ws, shift, heads, frames, dtype):
+    C = heads * 32
+    qkv = rnd(frames * Rr * Rr, 3 * C, dtype=dtype, seed=1)
+    rpb = rnd((2 * ws - 1) ** 2, heads, dtype=torch.float32, seed=2, scale=0.5)
+    out = torch.full((frames * Rr * Rr, C), float("nan"), dtype=dtype, device="cuda")
+    L().window_attn_fwd(qkv, rpb, out, frames, Rr, ws, shift, heads)
+    ref = torch.empty(frames * Rr * Rr, C, dtype=torch.float64)
+    R.window_attn_fwd(cpu(qkv), cpu(rpb), ref, frames, Rr, ws, shift, heads)
+    assert rel(out, ref) < TOL[dtype]
+    dout = rnd(frames * Rr * Rr, C, dtype=dtype, seed=3)
+    dqkv = torch.full_like(qkv, float("nan"))
+    L().window_attn_bwd(qkv, rpb, dout, dqkv, frames, Rr, ws, shift, heads)
+    r_d = torch.empty(frames * Rr * Rr, 3 * C, dtype=torch.float64)
+    R.window_attn_bwd(cpu(qkv), cpu(rpb), cpu(dout), r_d, frames, Rr, ws, shift, heads)
+    assert rel(dqkv, r_d) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("G,B,T,Ln,heads", [(2, 2, 10, 49, 2), (2, 1, 3, 30, 1), (1, 3, 16, 5, 3)])
+def test_temporal_attention(G, B, T, Ln, heads, dtype):
+    C = heads * 32
+    rows = G * B * T * Ln
+    qkv = rnd(rows, 3 * C, dtype=dtype, seed=1)
+    tbl = rnd(G, 2 * T - 1, heads, dtype=torch.float32, seed=2, scale=0.5)
+    out = torch.full((rows, C), float("nan"), dtype=dtype, device="cuda")
+    L().temporal_attn_fwd(qkv, tbl, out, G, B, T, Ln, heads)
+    ref = torch.empty(rows, C, dtype=torch.float64)
+    R.temporal_attn_fwd(cpu(qkv), cpu(tbl), ref, G, B, T, Ln, heads)
+    assert rel(out, ref) < TOL[dtype]
+    dout = rnd(rows, C, dtype=dtype, seed=3)
+    dqkv = torch.full_like(qkv, float("nan"))
+    dtbl = torch.zeros_like(tbl)
+    L().temporal_attn_bwd(qkv, tbl, dout, dqkv, dtbl, G, B, T, Ln, heads)
+    r_d, r_t = torch.empty(rows, 3 * C, dtype=torch.float64), torch.zeros(G, 2 * T - 1, heads, dtype=torch.float64)
+    R.temporal_attn_bwd(cpu(qkv), cpu(tbl), cpu(dout), r_d, r_t, G, B, T, Ln, heads)
+    assert rel(dqkv, r_d) < TOL[dtype]
+    assert rel(dtbl, r_t) < max(TOL[dtype], 1e-3)
+
+
+def _h_inputs(rows2, rp, r, dtype, seed):
+    """GELU-like features with the pad columns zero, [2*rows, rp]."""
+    h = torch.nn.functional.gelu(rnd(rows2, rp, dtype=torch.float32, seed=seed, scale=1.5)).to(dtype)
+    h[:, r:] = 0
+    return h
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("frames,Rr,ws,shift,rp,r", [(3, 14, 7, 0, 16, 12), (2, 14, 7, 3, 32, 24), (4, 7, 7, 0, 48, 48)])
+def test_xmodal_window(frames, Rr, ws, shift, rp, r, dtype):
+    rows = frames * Rr * Rr
+    h = _h_inputs(2 * rows, rp, r, dtype, 1)
+    hpre = rnd(2 * rows, rp, dtype=dtype, seed=2)
+    gate = torch.tensor([0.6, -0.4], device="cuda")
+    out, att = torch.full_like(h, float("nan")), torch.full_like(h, float("nan"))
+    L().xmodal_window_fwd(h, gate, out, att, frames, Rr, ws, shift, rp)
+    r_o, r_a = torch.empty(2 * rows, rp, dtype=torch.float64), torch.empty(2 * rows, rp, dtype=torch.float64)
+    R.xmodal_window_fwd(cpu(h), cpu(gate), r_o, r_a, frames, Rr, ws, shift, rp)
+    assert rel(out, r_o) < TOL[dtype] and rel(att, r_a) < TOL[dtype]
+    dout = rnd(2 * rows, rp, dtype=dtype, seed=3)
+    dh = torch.full_like(h, float("nan"))
+    dgate = torch.zeros(2, device="cuda")
+    L().xmodal_window_bwd(h, hpre, gate, att, dout, dh, dgate, frames, Rr, ws, shift, rp)
+    r_dh, r_dg = torch.empty(2 * rows, rp, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)
+    R.xmodal_window_bwd(cpu(h), cpu(hpre), cpu(gate), cpu(att), cpu(dout), r_dh, r_dg, frames, Rr, ws, shift, rp)
+    assert rel(dh, r_dh) < TOL[dtype]
+    assert rel(dgate, r_dg) < max(TOL[dtype], 1e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("frames,Ln,rp,r", [(2, 196, 16, 12), (3, 49, 48, 48), (1, 100, 96, 96), (1, 784, 32, 24), (1, 3136, 16, 12)])
+def test_xmodal_global(frames, Ln, rp, r, dtype):
+    rows = frames * Ln
+    h = _h_inputs(2 * rows, rp, r, dtype, 1)
+    hpre = rnd(2 * rows, rp, dtype=dtype, seed=2)
+    gate = torch.tensor([0.7, 0.3], device="cuda")
+    out, att = torch.full_like(h, float("nan")), torch.full_like(h, float("nan"))
+    lse = torch.empty(2 * rows, device="cuda")
+    L().xmodal_global_fwd(h, gate, out, att, lse, frames, Ln, rp)
+    r_o, r_a, r_l = (torch.empty(2 * rows, rp, dtype=torch.float64), torch.empty(2 * rows, rp, dtype=torch.float64),
+                     torch.empty(2 * rows, dtype=torch.float64))
+    R.xmodal_global_fwd(cpu(h), cpu(gate), r_o, r_a, r_l, frames, Ln, rp)
+    assert rel(out, r_o) < TOL[dtype] and rel(att, r_a) < TOL[dtype] and rel(lse, r_l) < TOL[dtype]
+    dout = rnd(2 * rows, rp, dtype=dtype, seed=3)
+    dh = torch.full_like(h, float("nan"))
+    dgate = torch.zeros(2, device="cuda")
+    work = torch.empty(2 * rows, device="cuda")
+    L().xmodal_global_bwd(h, hpre, gate, att, lse, dout, dh, dgate, work, frames, Ln, rp)
+    r_dh, r_dg = torch.empty(2 * rows, rp, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)
+    R.xmodal_global_bwd(cpu(h), cpu(hpre), cpu(gate), cpu(att), cpu(lse), cpu(dout), r_dh, r_dg, None, frames, Ln, rp)
+    assert rel(dh, r_dh) < TOL[dtype]
+    assert rel(dgate, r_dg) < max(TOL[dtype], 1e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_head_pool(dtype):
+    frames, N, C = 5, 49, 768
+    xn = rnd(2 * frames * N, C, dtype=dtype, seed=1)
+    feat = torch.empty(frames, 2 * C, dtype=dtype, device="cuda")
+    L().head_pool_fwd(xn, feat, frames, N, C)
+    ref = torch.empty(frames, 2 * C, dtype=torch.float64)
+    R.head_pool_fwd(cpu(xn), ref, frames, N, C)
+    assert rel(feat, ref) < TOL[dtype]
+    dfeat = rnd(frames, 2 * C, dtype=dtype, seed=2)
+    dxn = torch.empty_like(xn)
+    L().head_pool_bwd(dfeat, dxn, frames, N, C)
+    r_d = torch.empty(2 * frames * N, C, dtype=torch.float64)
+    R.head_pool_bwd(cpu(dfeat), r_d, frames, N, C)
+    assert rel(dxn, r_d) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pack_params(dtype):
+    lib = L()
+    src = rnd(12, 96, dtype=torch.float32, seed=1)
+    bias = rnd(12, dtype=torch.float32, seed=2)
+    w = torch.zeros(16, 96, dtype=dtype, device="cuda")
+    wt = torch.zeros(96, 16, dtype=dtype, device="cuda")
+    b = torch.zeros(16, device="cuda")
+    raw = lib.pack_entry(src, w, 12, 96, 96, 96, False, False) + lib.pack_entry(src, wt, 12, 96, 96, 16, True, False) + \
+        lib.pack_entry(bias, b, 1, 12, 12, 16, False, True)
+    table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    lib.pack_params(table, 3, lib.dt(dtype))
+    torch.cuda.synchronize()
+    assert torch.equal(w[:12], src.to(dtype)) and float(w[12:].abs().max()) == 0
+    assert torch.equal(wt[:, :12], src.to(dtype).t()) and float(wt[:, 12:].abs().max()) == 0
+    assert torch.equal(b[:12], bias) and float(b[12:].abs().max()) == 0
+
+
+def test_bad_arguments_fail_loudly():
+    lib = L()
+    x = torch.zeros(8, 100, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(lib.StgcmaError):
+        lib.gemm(x, x, x, 8, 100, 100)  # K % 8 != 0 for bf16
+    with pytest.raises(lib.StgcmaError):
+        lib.xmodal_global_fwd(x, torch.zeros(2, device="cuda"), x, x, torch.zeros(8, device="cuda"), 1, 4, 20)  # rp unsupported

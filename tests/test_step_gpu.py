@@ -1,0 +1,191 @@
+"""End-to-end parity of the CUDA train step (model/Swin_AVE.py -> libstgcma.so) on a real B200.
+
+Bars (BASELINE.json north_star), relative = max|got - ref| / max|ref| per tensor:
+  fp32-accumulate check mode (compute_dtype=float32): logits and every adapter/head gradient 1e-3
+  bf16 production mode       (compute_dtype=bfloat16): 2e-2
+against (a) the oracle run here on the CPU in fp64 and (b) the fixtures in tests/golden/ that were
+produced by the UNMODIFIED reference (oracle/make_goldens.py).  Plus size-independent properties at
+the full Swin-T width: clip independence (the data-parallel partition), fusion with zero gates ==
+multimodal, run-to-run determinism of the forward, linearity of the backward in dlogits.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import swin_ave_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+TINY = dict(img_size=112, num_frames=3, embed_dim=32, depths=[2, 2, 2], num_heads=[1, 2, 4],
+            adapter_mlp_ratio=[0.25, 0.25, 0.125], label_dim=7)
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def build(cfg_kw, mode, dtype, sd, drop_path_rate=0.0):
+    import model
+    m = model.Swin_AVE.SwinTransformer2D_Adapter_New(ftmode=mode, drop_path_rate=drop_path_rate, compute_dtype=dtype,
+                                                     patch_size=[1, 4, 4], pretrained=None, **cfg_kw).cuda()
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    m.mlp_head[1].eval()
+    for n, p in m.named_parameters():
+        p.requires_grad_(O.is_trainable(n))
+    return m
+
+
+def step(m, a, v, labels, mode):
+    m.zero_grad(set_to_none=True)
+    out = m(a.cuda(), v.cuda(), mode)
+    loss = torch.nn.CrossEntropyLoss()(out, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    return out.detach().cpu(), float(loss), {n: p.grad.detach().cpu() for n, p in m.named_parameters()
+                                             if p.requires_grad and p.grad is not None}
+
+
+def rel(got, ref):
+    return float((got.double() - ref.double()).abs().max() / ref.double().abs().max().clamp_min(1e-30))
+
+
+def check_grads(g, ref_g, tol, names=None):
+    bad = []
+    for n in (names or ref_g.keys()):
+        e = rel(g[n], ref_g[n])
+        if not e < tol:
+            bad.append((n, e))
+    assert not bad, f"{len(bad)} gradient tensors beyond {tol}: {bad[:8]}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["fusion", "multimodal"])
+def test_tiny_step_vs_oracle(mode, dtype):
+    cfg = O.SwinAVEConfig(**TINY)
+    sd = O.make_state(cfg, seed=3)
+    a, v, labels = O.make_inputs(cfg, 2, seed=3)
+    sd64 = {k: (t.double() if t.is_floating_point() else t) for k, t in sd.items()}
+    r_out, r_loss, r_g = O.train_step(sd64, a.double(), v.double(), labels.double(), cfg, mode)
+    m = build(TINY, mode, dtype, sd)
+    out, loss, g = step(m, a, v, labels, mode)
+    assert out.dtype == torch.float32
+    assert rel(out, r_out) < TOL[dtype]
+    assert abs(loss - float(r_loss)) < TOL[dtype] * max(1.0, abs(float(r_loss)))
+    assert set(r_g) <= set(g)
+    check_grads(g, r_g, TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion"])
+def test_step_vs_reference_golden(name, dtype):
+    fx = torch.load(os.path.join(GOLD, name + ".pt"))
+    cfg = O.SwinAVEConfig(**fx["cfg"])
+    sd = O.make_state(cfg, seed=fx["seed"])
+    a, v, labels = O.make_inputs(cfg, fx["batch"], seed=fx["seed"])
+    m = build(fx["cfg"], fx["mode"], dtype, sd)
+    out, loss, g = step(m, a, v, labels, fx["mode"])
+    assert rel(out, fx["logits"]) < TOL[dtype]
+    check_grads(g, fx["grads"], TOL[dtype])
+    # tensors too large for the fixture: L2 norm and a 64-element probe
+    from oracle.make_goldens import probe_index
+    bad = []
+    for n, nrm in fx["grad_norm"].items():
+        if n in fx["grads"]:
+            continue
+        got = g[n].double()
+        probe = got.reshape(-1)[probe_index(got.numel())]
+        scale = nrm / max(got.numel(), 1) ** 0.5
+        if abs(float(got.norm()) - nrm) > TOL[dtype] * nrm or float((probe - fx["grad_probe"][n]).abs().max()) > 10 * TOL[dtype] * scale:
+            bad.append(n)
+    assert not bad, bad[:8]
+
+
+def test_drop_path_and_dropout_replay():
+    """Stochastic layers on the GPU: the engine draws the masks, the oracle replays them (fp32 mode)."""
+    cfg = O.SwinAVEConfig(**TINY)
+    sd = O.make_state(cfg, seed=5)
+    a, v, labels = O.make_inputs(cfg, 2, seed=5)
+    m = build(TINY, "fusion", torch.float32, sd, drop_path_rate=0.5)
+    m.mlp_head[1].train()
+    torch.manual_seed(0)
+    out = m(a.cuda(), v.cuda(), "fusion")
+    saved = out.grad_fn.saved
+    B, T = 2, cfg.num_frames
+    masks = {}
+    for s in range(cfg.num_stages):
+        for i in range(0, cfg.depths[s], 2):
+            Ls = cfg.stage_res(s) ** 2
+            dp = saved["dp"].get((s, i))
+            masks[(s, i)] = (dp.view(2, B, T, Ls)[:, :, 0, :].reshape(2, B * Ls).cpu().double() if dp is not None
+                             else torch.ones(2, B * Ls, dtype=torch.float64))
+    keep = saved["keepmask"].cpu().double()
+    loss = torch.nn.CrossEntropyLoss()(out, labels.cuda())
+    loss.backward()
+    sd64 = {k: (t.double() if t.is_floating_point() else t) for k, t in sd.items()}
+    r_out, _, r_g = O.train_step(sd64, a.double(), v.double(), labels.double(), cfg, "fusion", drop_masks=masks, head_keep=keep)
+    assert rel(out.detach().cpu(), r_out) < 1e-3
+    check_grads({n: p.grad.cpu() for n, p in m.named_parameters() if p.requires_grad}, r_g, 1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_full_width_properties(dtype):
+    """Swin-T at full resolution (L = 3136 at stage 0), T = 10, B = 2: properties that need no oracle."""
+    kw = dict(img_size=224, num_frames=10, label_dim=29, **O.PRESETS["swin_t"])
+    cfg = O.SwinAVEConfig(**kw)
+    sd = O.make_state(cfg, seed=7)
+    a, v, labels = O.make_inputs(cfg, 2, seed=7)
+    m = build(kw, "fusion", dtype, sd)
+    out2, _, g2 = step(m, a, v, labels, "fusion")
+    assert torch.isfinite(out2).all() and all(torch.isfinite(t).all() for t in g2.values())
+    # (1) determinism of the forward
+    with torch.no_grad():
+        again = m(a.cuda(), v.cuda(), "fusion").cpu()
+    assert torch.equal(again, out2)
+    # (2) clips are independent: clip 0 alone gives clip 0's rows (this is what lets the step shard by clip)
+    with torch.no_grad():
+        out1 = m(a[:1].cuda(), v[:1].cuda(), "fusion").cpu()
+    assert rel(out1, out2[:10]) < 1e-6 or torch.equal(out1, out2[:10])
+    # (3) backward is linear in dlogits: scaling the loss by 8 scales every gradient by 8 (bf16 exact power of 2)
+    m.zero_grad(set_to_none=True)
+    out = m(a.cuda(), v.cuda(), "fusion")
+    (8.0 * torch.nn.CrossEntropyLoss()(out, labels.cuda())).backward()
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            assert rel(p.grad.cpu(), 8.0 * g2[n]) < 2e-3, n
+    # (4) zero gates: fusion == multimodal (exact in the reference)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "gate_" in n:
+                p.zero_()
+        f0 = m(a.cuda(), v.cuda(), "fusion").cpu()
+        mm = m(a.cuda(), v.cuda(), "multimodal").cpu()
+    assert rel(f0, mm) < 1e-6 or torch.equal(f0, mm)
+
+
+def test_caller_loop_autocast_gradscaler():
+    """The reference caller wraps the model in fp16 autocast + GradScaler + nn.DataParallel
+    (traintest_adapt_ave29.py:32-33,119,161-168): the drop-in must survive that unchanged."""
+    cfg = O.SwinAVEConfig(**TINY)
+    sd = O.make_state(cfg, seed=3)
+    a, v, labels = O.make_inputs(cfg, 2, seed=3)
+    m = build(TINY, "fusion", torch.bfloat16, sd)
+    dp = torch.nn.DataParallel(m, device_ids=[0])
+    params = [p for p in dp.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=5e-7, betas=(0.95, 0.999))
+    scaler = torch.amp.GradScaler("cuda")
+    before = [p.detach().clone() for p in params]
+    losses = []
+    for _ in range(3):
+        with torch.autocast("cuda"):
+            out = dp(a.cuda(), v.cuda(), "fusion")
+            loss = torch.nn.CrossEntropyLoss()(out, labels.cuda())
+        opt.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        losses.append(loss.item())
+    assert all(l == l for l in losses)
+    assert losses[-1] < losses[0], losses
+    assert any(not torch.equal(b, p.detach()) for b, p in zip(before, params))
+    key = next(iter(dp.state_dict()))
+    assert key.startswith("module.")
