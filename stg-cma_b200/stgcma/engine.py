@@ -314,7 +314,7 @@ class SwinAVEEngine:
                 L_.gemm(at, A["w1"], h, M, rp, C, bias=A["b1"], out_pre=hpre, groups=2, epi=L_.EPI_GELU)
                 if fusion:
                     h2, att = buf(k + "s_h2", M, rp), buf(k + "s_att", M, rp)
-                    L_.xmodal_window_fwd(h, p["gate"], h2, att, BT, R, ws, shift, rp)
+                    L_.xmodal_window_fwd(h, p["gate"], h2, att, BT, R, ws, shift, rp, r=p["r"])
                 else:
                     h2 = h
                 x2 = buf(k + "x2", M, C)
@@ -336,7 +336,7 @@ class SwinAVEEngine:
                 if fusion:
                     h2, att = buf(k + "g_h2", M, rp), buf(k + "g_att", M, rp)
                     lse = buf(k + "g_lse", 2 * BT * Ls, dtype=torch.float32)
-                    L_.xmodal_global_fwd(h, p["gate"], h2, att, lse, BT, Ls, rp)
+                    L_.xmodal_global_fwd(h, p["gate"], h2, att, lse, BT, Ls, rp, r=p["r"])
                 else:
                     h2 = h
                 x3 = buf(k + "x3", M, C)
@@ -481,7 +481,7 @@ class SwinAVEEngine:
                     L_.gemm(dx, A["w2t"], dh2, M, rp, C, groups=2)
                     work = buf(f"xwork{s}", 2 * BT * Ls, dtype=torch.float32)
                     L_.xmodal_global_bwd(slot(k + "g_h"), slot(k + "g_hpre"), p["gate"], slot(k + "g_att"), slot(k + "g_lse"),
-                                         dh2, dhpre, dgate2, work, BT, Ls, rp)
+                                         dh2, dhpre, dgate2, work, BT, Ls, rp, r=r)
                     h2 = slot(k + "g_h2")
                 else:
                     L_.gemm(dx, A["w2t"], dhpre, M, rp, C, groups=2, aux=slot(k + "g_hpre"), epi=L_.EPI_DGELU)
@@ -501,7 +501,7 @@ class SwinAVEEngine:
                 if fusion:
                     L_.gemm(dx2, A["w2t"], dh2, M, rp, C, groups=2)
                     L_.xmodal_window_bwd(slot(k + "s_h"), slot(k + "s_hpre"), p["gate"], slot(k + "s_att"), dh2, dhpre, dgate2,
-                                         BT, R, ws, shift, rp)
+                                         BT, R, ws, shift, rp, r=r)
                     h2 = slot(k + "s_h2")
                 else:
                     L_.gemm(dx2, A["w2t"], dhpre, M, rp, C, groups=2, aux=slot(k + "s_hpre"), epi=L_.EPI_DGELU)

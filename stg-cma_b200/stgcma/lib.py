@@ -91,13 +91,49 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _call(name, *args):
+_prof = None  # when a list: (name, start_event, end_event, flops, bytes) per ABI call
+
+
+def profile_start():
+    """Bracket every subsequent ABI call with CUDA events on the launching stream (bench.py uses this
+    for the per-kernel time shares and the roofline of the dominant kernel)."""
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """-> {kernel name: dict(ms, calls, flops, bytes)}; algorithmic flops / bytes as given by the wrappers."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, flops, nbytes in rec or []:
+        d = out.setdefault(name, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+        d["ms"] += e0.elapsed_time(e1)
+        d["calls"] += 1
+        d["flops"] += flops
+        d["bytes"] += nbytes
+    return out
+
+
+def _call(name, *args, cost=(0.0, 0.0)):
     global _launches
     lib = load()
-    rc = getattr(lib, name)(*args, _stream())  # every kernel entry point takes the stream last
+    stream = _stream()
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = getattr(lib, name)(*args, stream)  # every kernel entry point takes the stream last
     if rc != 0:
         raise StgcmaError(f"{name} failed ({rc}): {lib.stgcma_last_error().decode()}")
+    if _prof is not None:
+        e1.record()
+        _prof.append((name, e0, e1, float(cost[0]), float(cost[1])))
     _launches += 1
+
+
+def _es(t):
+    return t.element_size()
 
 
 _checked = set()
@@ -126,69 +162,88 @@ def require_device(*tensors):
 # thin typed wrappers (shapes are the caller's responsibility; see include/stgcma.h)
 # ---------------------------------------------------------------------------------------------
 def patch_embed_fwd(img, w, bias, gamma, beta, out, B, Cin, T, H, W, C):
+    tok = B * T * (H // 4) * (W // 4)
     _call("stgcma_patch_embed_fwd", _p(img), _p(w), _p(bias), _p(gamma), _p(beta), _p(out), B, Cin, T, H, W, C,
-          dt(out))
+          dt(out), cost=(2.0 * tok * Cin * 16 * C, 4.0 * B * Cin * T * H * W + tok * C * _es(out)))
 
 
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=0, R=0):
-    _call("stgcma_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, merge, R, dt(x))
+    _call("stgcma_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, merge, R, dt(x),
+          cost=(0.0, 2.0 * rows * C * _es(x)))
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0):
     _call("stgcma_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), rows, C, merge, R,
-          dt(x))
+          dt(x), cost=(0.0, (3.0 + (dres is not None)) * rows * C * _es(x)))
 
 
 def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, aux=None, out_pre=None, lda=None,
          ldw=None, ldo=None, groups=1, epi=EPI_LINEAR):
     _call("stgcma_gemm", _p(A), _p(W), _p(bias), _p(res1), _p(res2), _p(rowscale), _p(aux), _p(out), _p(out_pre), M, N,
-          K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A))
+          K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A),
+          cost=(2.0 * M * N * K, _es(A) * (M * K + groups * N * K + M * N * (
+              1.0 + (res1 is not None) + (res2 is not None) + (aux is not None) + (out_pre is not None)))))
 
 
 def gemm_tn(A, B, dW, M, Ka, Nb, *, lda, ldb, ldo, rowscale=None, csumA=None, csumB=None):
-    _call("stgcma_gemm_tn", _p(A), _p(B), _p(rowscale), _p(dW), _p(csumA), _p(csumB), M, Ka, Nb, lda, ldb, ldo, dt(A))
+    _call("stgcma_gemm_tn", _p(A), _p(B), _p(rowscale), _p(dW), _p(csumA), _p(csumB), M, Ka, Nb, lda, ldb, ldo, dt(A),
+          cost=(2.0 * M * Ka * Nb, _es(A) * M * (Ka + Nb)))
 
 
 def window_attn_fwd(qkv, rpb, out, frames, R, ws, shift, heads):
-    _call("stgcma_window_attn_fwd", _p(qkv), _p(rpb), _p(out), frames, R, ws, shift, heads, dt(qkv))
+    tok, C = frames * R * R, heads * 32
+    _call("stgcma_window_attn_fwd", _p(qkv), _p(rpb), _p(out), frames, R, ws, shift, heads, dt(qkv),
+          cost=(4.0 * tok * ws * ws * C, _es(qkv) * tok * 4 * C))
 
 
 def window_attn_bwd(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads):
-    _call("stgcma_window_attn_bwd", _p(qkv), _p(rpb), _p(dout), _p(dqkv), frames, R, ws, shift, heads, dt(qkv))
+    tok, C = frames * R * R, heads * 32
+    _call("stgcma_window_attn_bwd", _p(qkv), _p(rpb), _p(dout), _p(dqkv), frames, R, ws, shift, heads, dt(qkv),
+          cost=(8.0 * tok * ws * ws * C, _es(qkv) * tok * 7 * C))
 
 
 def temporal_attn_fwd(qkv, tbl, out, G, B, T, L, heads):
-    _call("stgcma_temporal_attn_fwd", _p(qkv), _p(tbl), _p(out), G, B, T, L, heads, dt(qkv))
+    tok, C = G * B * T * L, heads * 32
+    _call("stgcma_temporal_attn_fwd", _p(qkv), _p(tbl), _p(out), G, B, T, L, heads, dt(qkv),
+          cost=(4.0 * tok * T * C, _es(qkv) * tok * 4 * C))
 
 
 def temporal_attn_bwd(qkv, tbl, dout, dqkv, dtbl, G, B, T, L, heads):
-    _call("stgcma_temporal_attn_bwd", _p(qkv), _p(tbl), _p(dout), _p(dqkv), _p(dtbl), G, B, T, L, heads, dt(qkv))
+    tok, C = G * B * T * L, heads * 32
+    _call("stgcma_temporal_attn_bwd", _p(qkv), _p(tbl), _p(dout), _p(dqkv), _p(dtbl), G, B, T, L, heads, dt(qkv),
+          cost=(8.0 * tok * T * C, _es(qkv) * tok * 7 * C))
 
 
-def xmodal_window_fwd(h, gate, out, attn_out, frames, R, ws, shift, rp):
-    _call("stgcma_xmodal_window_fwd", _p(h), _p(gate), _p(out), _p(attn_out), frames, R, ws, shift, rp, dt(h))
+# `r` = un-padded hidden width, used only for the algorithmic-FLOP accounting (8 N r per token pair:
+# the reference's four bmm calls, Swin_AVE.py:753-757 / :801-805)
+def xmodal_window_fwd(h, gate, out, attn_out, frames, R, ws, shift, rp, r=None):
+    tok = frames * R * R
+    _call("stgcma_xmodal_window_fwd", _p(h), _p(gate), _p(out), _p(attn_out), frames, R, ws, shift, rp, dt(h),
+          cost=(8.0 * tok * ws * ws * (r or rp), _es(h) * 2 * tok * rp * 3))
 
 
-def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp):
+def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp, r=None):
+    tok = frames * R * R
     _call("stgcma_xmodal_window_bwd", _p(h), _p(hpre), _p(gate), _p(attn_out), _p(dout), _p(dh), _p(dgate), frames, R,
-          ws, shift, rp, dt(h))
+          ws, shift, rp, dt(h), cost=(16.0 * tok * ws * ws * (r or rp), _es(h) * 2 * tok * rp * 5))
 
 
-def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp):
-    _call("stgcma_xmodal_global_fwd", _p(h), _p(gate), _p(out), _p(attn_out), _p(lse), frames, L, rp, dt(h))
+def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp, r=None):
+    _call("stgcma_xmodal_global_fwd", _p(h), _p(gate), _p(out), _p(attn_out), _p(lse), frames, L, rp, dt(h),
+          cost=(8.0 * frames * L * L * (r or rp), _es(h) * 2 * frames * L * rp * 3))
 
 
-def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp):
+def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp, r=None):
     _call("stgcma_xmodal_global_bwd", _p(h), _p(hpre), _p(gate), _p(attn_out), _p(lse), _p(dout), _p(dh), _p(dgate),
-          _p(work), frames, L, rp, dt(h))
+          _p(work), frames, L, rp, dt(h), cost=(16.0 * frames * L * L * (r or rp), _es(h) * 2 * frames * L * rp * 5))
 
 
 def head_pool_fwd(xn, feat, frames, N, C):
-    _call("stgcma_head_pool_fwd", _p(xn), _p(feat), frames, N, C, dt(xn))
+    _call("stgcma_head_pool_fwd", _p(xn), _p(feat), frames, N, C, dt(xn), cost=(0.0, _es(xn) * 2 * frames * (N + 1) * C))
 
 
 def head_pool_bwd(dfeat, dxn, frames, N, C):
-    _call("stgcma_head_pool_bwd", _p(dfeat), _p(dxn), frames, N, C, dt(dxn))
+    _call("stgcma_head_pool_bwd", _p(dfeat), _p(dxn), frames, N, C, dt(dxn), cost=(0.0, _es(dxn) * 2 * frames * (N + 1) * C))
 
 
 PACK_ENTRY = struct.Struct("<QQiiqqii")  # mirrors StgcmaPackEntry (48 bytes)

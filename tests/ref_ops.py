@@ -220,14 +220,14 @@ def _xw(h, gate, frames, R, ws, shift, rp):
     return torch.stack((back(ov), back(oa))), torch.stack((back(a2v), back(v2a)))
 
 
-def xmodal_window_fwd(h, gate, out, attn_out, frames, R, ws, shift, rp):
+def xmodal_window_fwd(h, gate, out, attn_out, frames, R, ws, shift, rp, r=None):
     o, a = _xw(_c(h), _c(gate), frames, R, ws, shift, rp)
     out.copy_(o.reshape(out.shape))
     attn_out.copy_(a.reshape(attn_out.shape))
 
 
 @torch.enable_grad()
-def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp):
+def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp, r=None):
     hh = _c(h).detach().clone().requires_grad_(True)
     gg = _c(gate).detach().clone().requires_grad_(True)
     o, _ = _xw(hh, gg, frames, R, ws, shift, rp)
@@ -244,7 +244,7 @@ def _xg(h, gate, frames, L, rp):
     return torch.stack((ov, oa)), torch.stack((a2v, v2a)), torch.stack((lv, la))
 
 
-def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp):
+def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp, r=None):
     o, a, l = _xg(_c(h), _c(gate), frames, L, rp)
     out.copy_(o.reshape(out.shape))
     attn_out.copy_(a.reshape(attn_out.shape))
@@ -252,7 +252,7 @@ def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp):
 
 
 @torch.enable_grad()
-def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp):
+def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp, r=None):
     hh = _c(h).detach().clone().requires_grad_(True)
     gg = _c(gate).detach().clone().requires_grad_(True)
     o, _, _ = _xg(hh, gg, frames, L, rp)
