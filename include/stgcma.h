@@ -63,18 +63,22 @@ int stgcma_patch_embed_fwd(const float* img, const float* w, const float* bias, 
                            int dtype, void* stream);
 
 /* ---- nn.LayerNorm(C), eps 1e-5, frozen affine (norm1/norm2/norm; Swin_AVE.py:346,353,1314) --
+ * x is the RESIDUAL STREAM and has its own dtype `xdtype` (fp32 in both modes: the reference under the
+ * caller's autocast keeps the residual in fp32 too); y is an activation of type `dtype`.
  * merge = 0: x, y are [rows, C].
  * merge = 1: PatchMerging gather fused in (Swin_AVE.py:969-978): x is [frames, R, R, C/4],
  *            y is [frames*(R/2)^2, C] with channel blocks (2y,2x),(2y+1,2x),(2y,2x+1),(2y+1,2x+1);
  *            rows = frames*(R/2)^2.
  * mean / rstd fp32 [rows] are written when non-NULL (saved for backward).                    */
 int stgcma_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                         float* rstd, int64_t rows, int C, int merge, int R, int dtype, void* stream);
+                         float* rstd, int64_t rows, int C, int merge, int R, int xdtype, int dtype, void* stream);
 /* dx = dres + dLN/dx (dy)   -- no dgamma/dbeta: every LayerNorm on this path is frozen.
+ * dy has type `dydtype`; x, dres, dx have type `xdtype` (stream); dx_copy (optional) receives the same
+ * values in the activation type `dtype` -- the copy the next GEMM consumes as its A operand.
  * merge = 1 scatters back to [frames, R, R, C/4] (dres must then be NULL).                   */
 int stgcma_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
-                         const float* gamma, const void* dres, void* dx, int64_t rows, int C, int merge,
-                         int R, int dtype, void* stream);
+                         const float* gamma, const void* dres, void* dx, void* dx_copy, int64_t rows, int C,
+                         int merge, int R, int dydtype, int xdtype, int dtype, void* stream);
 
 /* ---- nn.Linear family: out[m, n] = epilogue( sum_k A[m,k] * W[g][n,k] + bias[g][n] ) --------
  * Replaces attn.qkv / attn.proj / mlp.fc1 / mlp.fc2 / downsample.reduction / adapter D_fc1,
@@ -83,10 +87,13 @@ int stgcma_layernorm_bwd(const void* dy, const void* x, const float* mean, const
  * group stride N*ldw), bias fp32 [groups, N] or NULL.  Rows are split in `groups` equal parts of
  * M/groups rows, part g using W[g] (groups = 2: per-modality adapter weights).
  * bf16 mode: tcgen05/TMEM kernel fed by TMA; needs K, lda, ldw multiples of 8 and 16-byte
- * aligned A / W; N multiple of 8.  res1/res2/aux/out/out_pre share row stride ldo.           */
+ * aligned A / W; N multiple of 8.  res1/res2/aux/out/out_pre share row stride ldo.
+ * out_dtype: type of `out` and `res1` -- `dtype`, or STGCMA_F32 when they are the fp32 residual
+ * stream (x_new = x + branch); res2 / aux / out_pre always have the activation type.          */
 int stgcma_gemm(const void* A, const void* W, const float* bias, const void* res1, const void* res2,
                 const float* rowscale, const void* aux, void* out, void* out_pre, int64_t M, int N, int K,
-                int64_t lda, int64_t ldw, int64_t ldo, int groups, int epilogue, int dtype, void* stream);
+                int64_t lda, int64_t ldw, int64_t ldo, int groups, int epilogue, int dtype, int out_dtype,
+                void* stream);
 
 /* ---- weight gradients of the trainable nn.Linear layers (adapters, head) -------------------
  * dW[i, j] += sum_m rowscale[m] * A[m, i] * B[m, j]   (i < Ka, j < Nb; dW fp32, row stride ldo)

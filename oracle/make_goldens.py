@@ -17,7 +17,7 @@ import torch
 
 from . import shim
 from . import swin_ave_oracle as O
-from .validate_oracle import CASES, build_reference, reference_step
+from .validate_oracle import CASES, STATE_KW, build_reference, reference_step
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 SEED = 3
@@ -33,12 +33,12 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for name, kw, batch, mode in CASES:
         cfg = O.SwinAVEConfig(**kw)
-        sd = O.make_state(cfg, seed=SEED, dtype=torch.float64)
+        sd = O.make_state(cfg, seed=SEED, dtype=torch.float64, **STATE_KW)
         a, v, labels = O.make_inputs(cfg, batch, seed=SEED, dtype=torch.float64)
         model = build_reference(cfg, mode).double()
         out, loss, grads = reference_step(model, sd, a, v, labels, mode)
         full = name.startswith("tiny")
-        fx = dict(name=name, cfg=kw, batch=batch, mode=mode, seed=SEED,
+        fx = dict(name=name, cfg=kw, batch=batch, mode=mode, seed=SEED, state_kw=dict(STATE_KW),
                   logits=out, loss=loss,
                   state_keys=list(sd.keys()),
                   state_shapes={k: tuple(t.shape) for k, t in sd.items()},

@@ -128,13 +128,27 @@ def window_token_index(R, ws, shift):
 # ----------------------------------------------------------------------------------------
 # deterministic synthetic weights / inputs
 # ----------------------------------------------------------------------------------------
-def make_state(cfg: SwinAVEConfig, seed=0, w_std=0.02, fc2_std=0.05, gate_lo=0.25, gate_hi=0.75,
-               dtype=torch.float32):
+def make_state(cfg: SwinAVEConfig, seed=0, w_std=0.02, gain=1.0, fc1_gain=1.2, fc2_gain=0.5, gate_lo=0.25, gate_hi=0.75,
+               dtype=torch.float32, bf16_exact=False):
     """Seeded synthetic weights under the reference's state_dict names (incl. buffers).
 
     Unlike the reference's init (Swin_AVE.py:1422-1468 zeroes every adapter D_fc2, :365-366
     zero gates) the adapters' second projections and the gates are NON-zero, otherwise
     dW(D_fc1), dgate and the whole cross-modal path are identically zero.
+
+    Every Linear is drawn with std = gain / sqrt(fan_in), so activations stay O(1) at every width
+    (Swin-T ... Swin-L) like in a trained network.  A fixed std (e.g. 0.05) makes the adapter
+    features grow with the stage width until the UNSCALED cross-modal logits hv.ha^T (Swin_AVE.py:753,
+    :801) reach |S| > 100 at stage 3: a softmax that sharp amplifies any input rounding (bf16: 2^-9
+    relative -> delta S ~ 0.4 -> tens of percent in P), i.e. an ill-conditioned test problem that no
+    reduced-precision implementation -- the reference's own fp16 autocast included -- can meet.  With the
+    defaults below the logits are O(1..10) and the cross-modal term still moves the logits by several
+    percent (tests/test_oracle_golden.py checks both).
+
+    bf16_exact=True rounds every floating-point tensor to a bf16-representable value (still stored in
+    `dtype`): the reference / oracle and the bf16 production path then consume IDENTICAL weights, so a
+    parity test measures the kernels and the activation-precision policy, not the (coherent, therefore
+    non-averaging) perturbation that quantising given fp32 weights to bf16 would add on top.
     """
     g = torch.Generator().manual_seed(seed)
     sd = OrderedDict()
@@ -146,8 +160,8 @@ def make_state(cfg: SwinAVEConfig, seed=0, w_std=0.02, fc2_std=0.05, gate_lo=0.2
         sd[prefix + ".weight"] = (1.0 + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)).to(dtype)
         sd[prefix + ".bias"] = rn(n, std=0.05)
 
-    def linear(prefix, out_f, in_f, bias=True, std=w_std):
-        sd[prefix + ".weight"] = rn(out_f, in_f, std=std)
+    def linear(prefix, out_f, in_f, bias=True, g_=gain):
+        sd[prefix + ".weight"] = rn(out_f, in_f, std=g_ / math.sqrt(in_f))
         if bias:
             sd[prefix + ".bias"] = rn(out_f, std=0.02)
 
@@ -170,8 +184,8 @@ def make_state(cfg: SwinAVEConfig, seed=0, w_std=0.02, fc2_std=0.05, gate_lo=0.2
             t_attn = (i % 2 == 0)
 
             def adapter(nm):
-                linear(p + nm + ".D_fc1", r, C, std=0.05)
-                linear(p + nm + ".D_fc2", C, r, std=fc2_std)
+                linear(p + nm + ".D_fc1", r, C, g_=fc1_gain)
+                linear(p + nm + ".D_fc2", C, r, g_=fc2_gain)
 
             if t_attn:
                 adapter("T_Adapter")
@@ -179,16 +193,16 @@ def make_state(cfg: SwinAVEConfig, seed=0, w_std=0.02, fc2_std=0.05, gate_lo=0.2
             ln(p + "norm1", C)
             sd[p + "attn.relative_position_bias_table"] = rn((2 * ws - 1) * (2 * ws - 1), heads, std=0.2)
             sd[p + "attn.relative_position_index"] = relative_position_index(ws)
-            linear(p + "attn.qkv", 3 * C, C, std=0.05)
-            linear(p + "attn.proj", C, C, std=0.05)
+            linear(p + "attn.qkv", 3 * C, C)
+            linear(p + "attn.proj", C, C)
             if t_attn:
                 sd[p + "attn.temporal_position_bias_table"] = rn(2 * T - 1, heads, std=0.2)
                 sd[p + "attn.t_relative_coords"] = temporal_relative_coords(T)
                 sd[p + "attn.temporal_position_bias_table_audio"] = rn(2 * T - 1, heads, std=0.2)
                 sd[p + "attn.t_relative_coords_a"] = temporal_relative_coords(T)
             ln(p + "norm2", C)
-            linear(p + "mlp.fc1", hid, C, std=0.05)
-            linear(p + "mlp.fc2", C, hid, std=0.05)
+            linear(p + "mlp.fc1", hid, C)
+            linear(p + "mlp.fc2", C, hid)
             adapter("S_Adapter")
             adapter("S_Adapter2")
             adapter("S_Adapter_Audio")
@@ -199,13 +213,17 @@ def make_state(cfg: SwinAVEConfig, seed=0, w_std=0.02, fc2_std=0.05, gate_lo=0.2
                 sd[p + "attn_mask"] = shifted_window_mask(R, ws, shift).to(dtype)
         if s < cfg.num_stages - 1:
             p = f"layers.{s}.downsample."
-            linear(p + "reduction", 2 * C, 4 * C, bias=False, std=0.03)
+            linear(p + "reduction", 2 * C, 4 * C, bias=False)
             ln(p + "norm", 4 * C)
 
     Cf = cfg.stage_dim(cfg.num_stages - 1)
     ln("norm", Cf)
-    linear("mlp_head.0", 512, 2 * Cf, std=0.03)
-    linear("mlp_head.2", cfg.label_dim, 512, std=0.05)
+    linear("mlp_head.0", 512, 2 * Cf)
+    linear("mlp_head.2", cfg.label_dim, 512)
+    if bf16_exact:
+        for k_, t_ in sd.items():
+            if t_.is_floating_point() and not is_buffer(k_):
+                sd[k_] = t_.to(torch.bfloat16).to(dtype)
     return sd
 
 

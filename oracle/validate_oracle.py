@@ -27,7 +27,12 @@ CASES = [
     ("tiny3stage_multimodal", dict(img_size=112, num_frames=3, embed_dim=32, depths=[2, 2, 2], num_heads=[1, 2, 4],
                                    adapter_mlp_ratio=[0.25, 0.25, 0.125], label_dim=7), 2, "multimodal"),
     ("swin_t_T2_fusion", dict(img_size=224, num_frames=2, label_dim=29, **O.PRESETS["swin_t"]), 1, "fusion"),
+    # BASELINE.json configs[0]: AVE 29-class Swin-T, batch 2, 10 frames 224^2 (the reference's CPU-runnable case)
+    ("swin_t_T10_B2_fusion", dict(img_size=224, num_frames=10, label_dim=29, **O.PRESETS["swin_t"]), 2, "fusion"),
 ]
+# every case uses bf16-representable weights (make_state docstring): the same fixture then serves the fp32
+# check mode (1e-3) and the bf16 production mode (2e-2) with IDENTICAL weights on both sides
+STATE_KW = dict(bf16_exact=True)
 
 
 def build_reference(cfg, mode):
@@ -70,7 +75,7 @@ def main():
     worst = 0.0
     for name, kw, batch, mode in CASES:
         cfg = O.SwinAVEConfig(**kw)
-        sd = O.make_state(cfg, seed=3, dtype=torch.float64)
+        sd = O.make_state(cfg, seed=3, dtype=torch.float64, **STATE_KW)
         a, v, labels = O.make_inputs(cfg, batch, seed=3, dtype=torch.float64)
         t0 = time.time()
         model = build_reference(cfg, mode).double()

@@ -68,6 +68,28 @@ template <> struct Vec<bf16> {
   }
 };
 
+// 8 consecutive elements <-> fp32 registers (16 B for bf16, 2 x 16 B for fp32); p must be 16 B aligned.
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  Vec<bf16> t;
+  t.load(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = t.v[i];
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  Vec<bf16> t;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t.v[i] = v[i];
+  t.store(p);
+}
+
 // ---- math ------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
@@ -109,6 +131,7 @@ struct EpiParams {
   void* out_pre;          // GELU: optional pre-activation output
   int64_t ldo;
   int mode;
+  int out_f32;            // 1: `out` and `res1` are fp32 (the residual stream) whatever the activation dtype
 };
 
 }  // namespace stgcma

@@ -8,7 +8,7 @@ namespace stgcma {
 // =========================================================================================
 // LayerNorm: one warp per row.
 // =========================================================================================
-template <typename T, bool MERGE>
+template <bool MERGE>
 struct RowAddr {
   // element offset of channel c of logical row `row`
   int64_t base[4];
@@ -39,42 +39,42 @@ struct RowAddr {
   }
 };
 
-template <typename T, bool MERGE>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, T* __restrict__ y,
+// TX: type of x (the residual stream), TY: type of y.  8 channels per lane per step.
+template <typename TX, typename TY, bool MERGE>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, TY* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      int64_t rows, int C, int R) {
-  constexpr int V = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  RowAddr<T, MERGE> addr(row, C, R);
+  RowAddr<MERGE> addr(row, C, R);
   float s = 0.f;
-  for (int c = lane * V; c < C; c += 32 * V) {
-    Vec<T> t;
-    t.load(x + addr.at(c));
+  for (int c = lane * 8; c < C; c += 256) {
+    float t[8];
+    load8(x + addr.at(c), t);
 #pragma unroll
-    for (int i = 0; i < V; ++i) s += t.v[i];
+    for (int i = 0; i < 8; ++i) s += t[i];
   }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
-  for (int c = lane * V; c < C; c += 32 * V) {
-    Vec<T> t;
-    t.load(x + addr.at(c));
+  for (int c = lane * 8; c < C; c += 256) {
+    float t[8];
+    load8(x + addr.at(c), t);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float d = t.v[i] - mean;
+    for (int i = 0; i < 8; ++i) {
+      const float d = t[i] - mean;
       q += d * d;
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
-  T* yrow = y + row * (int64_t)C;
-  for (int c = lane * V; c < C; c += 32 * V) {
-    Vec<T> t;
-    t.load(x + addr.at(c));
+  TY* yrow = y + row * (int64_t)C;
+  for (int c = lane * 8; c < C; c += 256) {
+    float t[8];
+    load8(x + addr.at(c), t);
 #pragma unroll
-    for (int i = 0; i < V; ++i) t.v[i] = (t.v[i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i);
-    t.store(yrow + c);
+    for (int i = 0; i < 8; ++i) t[i] = (t[i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i);
+    store8(yrow + c, t);
   }
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
@@ -82,72 +82,73 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
   }
 }
 
-template <typename T, bool MERGE>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+// TD: type of dy, TX: type of x / dres / dx (stream), TC: type of the optional operand copy of dx.
+template <typename TD, typename TX, typename TC, bool MERGE>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TD* __restrict__ dy, const TX* __restrict__ x,
                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                                                     const float* __restrict__ gamma, const T* dres,
-                                                     T* dx, int64_t rows, int C, int R) {  // dres may alias dx
-  constexpr int V = Vec<T>::N;
+                                                     const float* __restrict__ gamma, const TX* dres, TX* dx,
+                                                     TC* __restrict__ dx_copy, int64_t rows, int C, int R) {  // dres may alias dx
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  RowAddr<T, MERGE> addr(row, C, R);
+  RowAddr<MERGE> addr(row, C, R);
   const float mean = mean_in[row], rstd = rstd_in[row];
-  const T* dyrow = dy + row * (int64_t)C;
+  const TD* dyrow = dy + row * (int64_t)C;
   float s1 = 0.f, s2 = 0.f;
-  for (int c = lane * V; c < C; c += 32 * V) {
-    Vec<T> g, t;
-    g.load(dyrow + c);
-    t.load(x + addr.at(c));
+  for (int c = lane * 8; c < C; c += 256) {
+    float g[8], t[8];
+    load8(dyrow + c, g);
+    load8(x + addr.at(c), t);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float gg = g.v[i] * __ldg(gamma + c + i);
+    for (int i = 0; i < 8; ++i) {
+      const float gg = g[i] * __ldg(gamma + c + i);
       s1 += gg;
-      s2 += gg * (t.v[i] - mean) * rstd;
+      s2 += gg * (t[i] - mean) * rstd;
     }
   }
   s1 = warp_sum(s1) / (float)C;
   s2 = warp_sum(s2) / (float)C;
-  for (int c = lane * V; c < C; c += 32 * V) {
-    Vec<T> g, t, o;
-    g.load(dyrow + c);
+  for (int c = lane * 8; c < C; c += 256) {
+    float g[8], t[8], o[8];
+    load8(dyrow + c, g);
     const int64_t off = addr.at(c);
-    t.load(x + off);
-    if (dres) o.load(dres + off);
+    load8(x + off, t);
+    if (dres) load8(dres + off, o);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float gg = g.v[i] * __ldg(gamma + c + i);
-      const float xh = (t.v[i] - mean) * rstd;
+    for (int i = 0; i < 8; ++i) {
+      const float gg = g[i] * __ldg(gamma + c + i);
+      const float xh = (t[i] - mean) * rstd;
       const float d = rstd * (gg - s1 - xh * s2);
-      o.v[i] = dres ? o.v[i] + d : d;
+      o[i] = dres ? o[i] + d : d;
     }
-    o.store(dx + off);
+    store8(dx + off, o);
+    if (dx_copy) store8(dx_copy + off, o);
   }
 }
 
-template <typename T>
+template <typename TX, typename TY>
 static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                          int64_t rows, int C, int merge, int R, cudaStream_t st) {
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div(rows, wpb)), block(wpb * 32);
   if (merge)
-    ln_fwd_kernel<T, true><<<grid, block, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, C, R);
+    ln_fwd_kernel<TX, TY, true><<<grid, block, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, C, R);
   else
-    ln_fwd_kernel<T, false><<<grid, block, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, C, R);
+    ln_fwd_kernel<TX, TY, false><<<grid, block, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean, rstd, rows, C, R);
   return check_launch("layernorm_fwd");
 }
 
-template <typename T>
+template <typename TD, typename TX, typename TC>
 static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                         const void* dres, void* dx, int64_t rows, int C, int merge, int R, cudaStream_t st) {
+                         const void* dres, void* dx, void* dx_copy, int64_t rows, int C, int merge, int R, cudaStream_t st) {
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div(rows, wpb)), block(wpb * 32);
   if (merge)
-    ln_bwd_kernel<T, true><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres,
-                                                   (T*)dx, rows, C, R);
+    ln_bwd_kernel<TD, TX, TC, true><<<grid, block, 0, st>>>((const TD*)dy, (const TX*)x, mean, rstd, gamma, (const TX*)dres,
+                                                            (TX*)dx, (TC*)dx_copy, rows, C, R);
   else
-    ln_bwd_kernel<T, false><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres,
-                                                    (T*)dx, rows, C, R);
+    ln_bwd_kernel<TD, TX, TC, false><<<grid, block, 0, st>>>((const TD*)dy, (const TX*)x, mean, rstd, gamma, (const TX*)dres,
+                                                             (TX*)dx, (TC*)dx_copy, rows, C, R);
   return check_launch("layernorm_bwd");
 }
 
@@ -288,26 +289,33 @@ extern "C" int stgcma_pack_params(const StgcmaPackEntry* table_dev, int n, int d
 }
 
 extern "C" int stgcma_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                                    float* rstd, int64_t rows, int C, int merge, int R, int dtype, void* stream) {
+                                    float* rstd, int64_t rows, int C, int merge, int R, int xdtype, int dtype, void* stream) {
   STG_REQUIRE(rows > 0 && C > 0, "layernorm_fwd: empty input");
   STG_REQUIRE(C % 8 == 0 && (!merge || (C % 32 == 0 && R % 2 == 0)), "layernorm_fwd: C=%d must be a multiple of 8 (32 when merging)", C);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == STGCMA_F32) return ln_fwd_launch<float>(x, gamma, beta, y, mean, rstd, rows, C, merge, R, st);
-  if (dtype == STGCMA_BF16) return ln_fwd_launch<bf16>(x, gamma, beta, y, mean, rstd, rows, C, merge, R, st);
-  STG_REQUIRE(false, "layernorm_fwd: bad dtype %d", dtype);
+  if (xdtype == STGCMA_F32 && dtype == STGCMA_F32) return ln_fwd_launch<float, float>(x, gamma, beta, y, mean, rstd, rows, C, merge, R, st);
+  if (xdtype == STGCMA_F32 && dtype == STGCMA_BF16) return ln_fwd_launch<float, bf16>(x, gamma, beta, y, mean, rstd, rows, C, merge, R, st);
+  if (xdtype == STGCMA_BF16 && dtype == STGCMA_BF16) return ln_fwd_launch<bf16, bf16>(x, gamma, beta, y, mean, rstd, rows, C, merge, R, st);
+  STG_REQUIRE(false, "layernorm_fwd: unsupported dtypes x=%d y=%d", xdtype, dtype);
 }
 
 extern "C" int stgcma_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
-                                    const float* gamma, const void* dres, void* dx, int64_t rows, int C, int merge,
-                                    int R, int dtype, void* stream) {
+                                    const float* gamma, const void* dres, void* dx, void* dx_copy, int64_t rows, int C,
+                                    int merge, int R, int dydtype, int xdtype, int dtype, void* stream) {
   STG_REQUIRE(rows > 0 && C > 0, "layernorm_bwd: empty input");
   STG_REQUIRE(C % 8 == 0 && (!merge || (C % 32 == 0 && R % 2 == 0)), "layernorm_bwd: C=%d must be a multiple of 8 (32 when merging)", C);
   STG_REQUIRE(!(merge && dres), "layernorm_bwd: dres is not supported together with merge");
   STG_REQUIRE(mean && rstd, "layernorm_bwd: saved statistics required");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == STGCMA_F32) return ln_bwd_launch<float>(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge, R, st);
-  if (dtype == STGCMA_BF16) return ln_bwd_launch<bf16>(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge, R, st);
-  STG_REQUIRE(false, "layernorm_bwd: bad dtype %d", dtype);
+#define LN_BWD_CASE(DY, X, CP, TD, TX, TC)                              \
+  if (dydtype == DY && xdtype == X && dtype == CP)                      \
+    return ln_bwd_launch<TD, TX, TC>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, merge, R, st);
+  LN_BWD_CASE(STGCMA_F32, STGCMA_F32, STGCMA_F32, float, float, float)
+  LN_BWD_CASE(STGCMA_F32, STGCMA_F32, STGCMA_BF16, float, float, bf16)
+  LN_BWD_CASE(STGCMA_BF16, STGCMA_F32, STGCMA_BF16, bf16, float, bf16)
+  LN_BWD_CASE(STGCMA_BF16, STGCMA_BF16, STGCMA_BF16, bf16, bf16, bf16)
+#undef LN_BWD_CASE
+  STG_REQUIRE(false, "layernorm_bwd: unsupported dtypes dy=%d x=%d copy=%d", dydtype, xdtype, dtype);
 }
 
 extern "C" int stgcma_patch_embed_fwd(const float* img, const float* w, const float* bias, const float* gamma,

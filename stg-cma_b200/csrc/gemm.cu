@@ -44,11 +44,11 @@ __device__ __forceinline__ void epi_elem(const EpiParams& p, int64_t row, int co
   }
 }
 
-// 8 consecutive bf16 columns of one row, 128-bit accesses.
+// 8 consecutive columns of one row, 128-bit accesses.  Activation tensors (res2 / aux / out_pre) are bf16;
+// `out` and `res1` are bf16, or fp32 when p.out_f32 (the residual stream).
 __device__ __forceinline__ void epi_vec8(const EpiParams& p, int64_t row, int col, float (&v)[8]) {
   const int64_t off = row * p.ldo + col;
-  bf16* out = reinterpret_cast<bf16*>(p.out);
-  Vec<bf16> o;
+  float o[8];
   if (p.rowscale) {
     const float s = p.rowscale[row];
 #pragma unroll
@@ -57,43 +57,41 @@ __device__ __forceinline__ void epi_vec8(const EpiParams& p, int64_t row, int co
   switch (p.mode) {
     case STGCMA_EPI_LINEAR: {
       if (p.res1) {
-        Vec<bf16> r;
-        r.load(reinterpret_cast<const bf16*>(p.res1) + off);
+        float r[8];
+        if (p.out_f32) load8(reinterpret_cast<const float*>(p.res1) + off, r);
+        else load8(reinterpret_cast<const bf16*>(p.res1) + off, r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r.v[i];
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
       }
       if (p.res2) {
-        Vec<bf16> r;
-        r.load(reinterpret_cast<const bf16*>(p.res2) + off);
+        float r[8];
+        load8(reinterpret_cast<const bf16*>(p.res2) + off, r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r.v[i];
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = v[i];
+      for (int i = 0; i < 8; ++i) o[i] = v[i];
     } break;
     case STGCMA_EPI_GELU: {
-      if (p.out_pre) {
+      if (p.out_pre) store8(reinterpret_cast<bf16*>(p.out_pre) + off, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = v[i];
-        o.store(reinterpret_cast<bf16*>(p.out_pre) + off);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = gelu_erf(v[i]);
+      for (int i = 0; i < 8; ++i) o[i] = gelu_erf(v[i]);
     } break;
     case STGCMA_EPI_DGELU: {
-      Vec<bf16> a;
-      a.load(reinterpret_cast<const bf16*>(p.aux) + off);
+      float a[8];
+      load8(reinterpret_cast<const bf16*>(p.aux) + off, a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = v[i] * gelu_erf_grad(a.v[i]);
+      for (int i = 0; i < 8; ++i) o[i] = v[i] * gelu_erf_grad(a[i]);
     } break;
     default: {
-      Vec<bf16> a;
-      a.load(reinterpret_cast<const bf16*>(p.aux) + off);
+      float a[8];
+      load8(reinterpret_cast<const bf16*>(p.aux) + off, a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = v[i] * a.v[i];
+      for (int i = 0; i < 8; ++i) o[i] = v[i] * a[i];
     } break;
   }
-  o.store(out + off);
+  if (p.out_f32) store8(reinterpret_cast<float*>(p.out) + off, o);
+  else store8(reinterpret_cast<bf16*>(p.out) + off, o);
 }
 
 // =========================================================================================
@@ -609,7 +607,9 @@ using namespace stgcma;
 
 extern "C" int stgcma_gemm(const void* A, const void* W, const float* bias, const void* res1, const void* res2,
                            const float* rowscale, const void* aux, void* out, void* out_pre, int64_t M, int N, int K,
-                           int64_t lda, int64_t ldw, int64_t ldo, int groups, int epilogue, int dtype, void* stream) {
+                           int64_t lda, int64_t ldw, int64_t ldo, int groups, int epilogue, int dtype, int out_dtype,
+                           void* stream) {
+  STG_REQUIRE(out_dtype == dtype || out_dtype == STGCMA_F32, "gemm: out_dtype must be the activation dtype or fp32");
   STG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
   STG_REQUIRE(groups >= 1 && M % groups == 0, "gemm: M=%lld not divisible by groups=%d", (long long)M, groups);
   STG_REQUIRE(epilogue >= STGCMA_EPI_LINEAR && epilogue <= STGCMA_EPI_MULAUX, "gemm: bad epilogue %d", epilogue);
@@ -619,6 +619,7 @@ extern "C" int stgcma_gemm(const void* A, const void* W, const float* bias, cons
   EpiParams ep;
   ep.bias = bias; ep.res1 = res1; ep.res2 = res2; ep.rowscale = rowscale; ep.aux = aux;
   ep.out = out; ep.out_pre = out_pre; ep.ldo = ldo; ep.mode = epilogue;
+  ep.out_f32 = (out_dtype == STGCMA_F32);
   if (dtype == STGCMA_F32) {
     const int64_t gr = M / groups;
     dim3 grid((unsigned)ceil_div(gr, 64), (unsigned)ceil_div(N, 64), groups);
@@ -629,7 +630,9 @@ extern "C" int stgcma_gemm(const void* A, const void* W, const float* bias, cons
   STG_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm(bf16): K=%d lda=%lld ldw=%lld must be multiples of 8", K,
               (long long)lda, (long long)ldw);
   STG_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "gemm(bf16): N=%d ldo=%lld must be multiples of 8", N, (long long)ldo);
-  STG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
+  STG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                  ((uintptr_t)res1 & 15) == 0 && ((uintptr_t)res2 & 15) == 0 && ((uintptr_t)aux & 15) == 0 &&
+                  ((uintptr_t)out_pre & 15) == 0,
               "gemm(bf16): operands must be 16-byte aligned");
   return tc::launch(A, W, M, N, K, lda, ldw, groups, ep, st);
 }

@@ -68,6 +68,14 @@ class SwinAVEEngine:
     # ------------------------------------------------------------------------------------------
     # parameters
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def stream_dtype(adt):
+        """dtype of the residual stream x / dx.  fp32 in both modes: the reference under the caller's autocast
+        also keeps the residual in fp32 (LayerNorm and the residual adds run in fp32, only Linear / bmm
+        outputs are half), and a bf16 stream re-rounds the sum once per sub-block, which alone puts
+        adapter gradients 3-5 % off after 12 blocks (measured)."""
+        return torch.float32 if adt == torch.bfloat16 else adt
+
     def _blocks(self):
         for s, layer in enumerate(self.m.layers):
             for i, blk in enumerate(layer.blocks):
@@ -204,13 +212,16 @@ class SwinAVEEngine:
         nl = h2.weight.shape[0]
         lp = _rup(nl, 16)
         F2, Hd = h0.weight.shape[1], h0.weight.shape[0]
-        hd = dict(lp=lp, nl=nl, w0=z(Hd, F2), w0t=z(F2, Hd), b0=z(Hd, dtype=torch.float32), w2=z(lp, Hd), w2t=z(Hd, lp),
-                  b2=z(lp, dtype=torch.float32))
-        add(h0.weight.data, hd["w0"], Hd, F2, F2, F2)
-        add(h0.weight.data, hd["w0t"], Hd, F2, F2, Hd, transpose=True)
+        # the head runs in fp32 in both modes (tiny: B*T rows): its tensors sit at the root of the backward,
+        # where a rounding error is shared by every gradient downstream
+        f32 = torch.float32
+        hd = dict(lp=lp, nl=nl, w0=z(Hd, F2, dtype=f32), w0t=z(F2, Hd, dtype=f32), b0=z(Hd, dtype=f32),
+                  w2=z(lp, Hd, dtype=f32), w2t=z(Hd, lp, dtype=f32), b2=z(lp, dtype=f32))
+        add(h0.weight.data, hd["w0"], Hd, F2, F2, F2, f32=True)
+        add(h0.weight.data, hd["w0t"], Hd, F2, F2, Hd, transpose=True, f32=True)
         add(h0.bias.data, hd["b0"], 1, Hd, Hd, Hd, f32=True)
-        add(h2.weight.data, hd["w2"], nl, Hd, Hd, Hd)
-        add(h2.weight.data, hd["w2t"], nl, Hd, Hd, lp, transpose=True)
+        add(h2.weight.data, hd["w2"], nl, Hd, Hd, Hd, f32=True)
+        add(h2.weight.data, hd["w2t"], nl, Hd, Hd, lp, transpose=True, f32=True)
         add(h2.bias.data, hd["b2"], 1, nl, nl, lp, f32=True)
         pk["head"] = hd
         raw = b"".join(entries)
@@ -252,7 +263,8 @@ class SwinAVEEngine:
         BT = B * T
         frames2 = 2 * BT
         training = m.training
-        sv = dict(B=B, mode=mode, gen=self.generation, dp={}, dev=dev, adt=adt)
+        sdt = self.stream_dtype(adt)   # residual stream x: fp32 even in bf16 mode
+        sv = dict(B=B, mode=mode, gen=self.generation, dp={}, dev=dev, adt=adt, sdt=sdt)
 
         def buf(name, *shape, dtype=adt, zero=False):
             return ar.get(name, shape, dtype, dev, zero)
@@ -260,7 +272,7 @@ class SwinAVEEngine:
         # ---- patch embed (video rows, then audio rows) ----
         C0, R0 = cfg.stage_dim(0), cfg.stage_res(0)
         L0 = R0 * R0
-        x = buf("x_in", 2 * BT * L0, C0)
+        x = buf("x_in", 2 * BT * L0, C0, dtype=sdt)
         pe, pa = fz["patch_embed"], fz["patch_embed_audio"]
         L_.patch_embed_fwd(v32, pe["w"], pe["b"], pe["g"], pe["beta"], x[:BT * L0], B, 3, T, H, W, C0)
         L_.patch_embed_fwd(a32, pa["w"], pa["b"], pa["g"], pa["beta"], x[BT * L0:], B, 1, T, H, W, C0)
@@ -295,7 +307,7 @@ class SwinAVEEngine:
                         mask = torch.empty(2, B, 1, Ls, device=dev, dtype=torch.float32).bernoulli_(keep).div_(keep)
                         dp = mask.expand(2, B, T, Ls).contiguous().view(-1)
                     sv["dp"][(s, i)] = dp
-                    x1 = buf(k + "x1", M, C)
+                    x1 = buf(k + "x1", M, C, dtype=sdt)
                     L_.gemm(h, A["w2"], x1, M, C, rp, bias=A["b2"], res1=x, rowscale=dp, groups=2)
                     sv[k + "x0"] = x
                     x = x1
@@ -317,7 +329,7 @@ class SwinAVEEngine:
                     L_.xmodal_window_fwd(h, p["gate"], h2, att, BT, R, ws, shift, rp, r=p["r"])
                 else:
                     h2 = h
-                x2 = buf(k + "x2", M, C)
+                x2 = buf(k + "x2", M, C, dtype=sdt)
                 L_.gemm(h2, A["w2"], x2, M, C, rp, bias=A["b2"], res1=x, res2=at, groups=2)
                 sv[k + "x1"] = x
                 x = x2
@@ -339,7 +351,7 @@ class SwinAVEEngine:
                     L_.xmodal_global_fwd(h, p["gate"], h2, att, lse, BT, Ls, rp, r=p["r"])
                 else:
                     h2 = h
-                x3 = buf(k + "x3", M, C)
+                x3 = buf(k + "x3", M, C, dtype=sdt)
                 L_.gemm(h2, A["w2"], x3, M, C, rp, bias=A["b2"], res1=x, res2=y, groups=2)
                 sv[k + "x2"] = x
                 x = x3
@@ -350,7 +362,7 @@ class SwinAVEEngine:
                 xm = buf(f"xm{s}", Mn, 4 * C)
                 mean, rstd = buf(f"m{s}_mean", Mn, dtype=torch.float32), buf(f"m{s}_rstd", Mn, dtype=torch.float32)
                 L_.layernorm_fwd(x, mg["g"], mg["b"], xm, mean, rstd, Mn, 4 * C, merge=1, R=R)
-                xnext = buf(f"m{s}_out", Mn, 2 * C)
+                xnext = buf(f"m{s}_out", Mn, 2 * C, dtype=sdt)
                 L_.gemm(xm, mg["w"], xnext, Mn, 2 * C, 4 * C)
                 sv[f"m{s}_in"] = x
                 x = xnext
@@ -360,26 +372,27 @@ class SwinAVEEngine:
         Ls = R * R
         M = frames2 * Ls
         hd = pk["head"]
-        xn = buf("h_xn", M, C)
+        f32 = torch.float32
+        xn = buf("h_xn", M, C, dtype=f32)
         mean, rstd = buf("h_mean", M, dtype=torch.float32), buf("h_rstd", M, dtype=torch.float32)
         L_.layernorm_fwd(x, fz["norm"]["g"], fz["norm"]["b"], xn, mean, rstd, M, C)
-        feat = buf("h_feat", BT, 2 * C)
+        feat = buf("h_feat", BT, 2 * C, dtype=f32)
         L_.head_pool_fwd(xn, feat, BT, Ls, C)
         Hd = hd["w0"].shape[0]
-        hh = buf("h_hidden", BT, Hd)
+        hh = buf("h_hidden", BT, Hd, dtype=f32)
         drop = m.mlp_head[1]
         keepmask = None
         if drop.training and drop.p > 0.0:
-            keepmask = torch.empty(BT, Hd, device=dev, dtype=torch.float32).bernoulli_(1.0 - drop.p).div_(1.0 - drop.p).to(adt)
+            keepmask = torch.empty(BT, Hd, device=dev, dtype=torch.float32).bernoulli_(1.0 - drop.p).div_(1.0 - drop.p)
             L_.gemm(feat, hd["w0"], hh, BT, Hd, 2 * C, bias=hd["b0"], aux=keepmask, epi=L_.EPI_MULAUX)
         else:
             L_.gemm(feat, hd["w0"], hh, BT, Hd, 2 * C, bias=hd["b0"])
         sv["keepmask"] = keepmask
         lp, nl = hd["lp"], hd["nl"]
-        logits_p = buf("h_logits", BT, lp)
+        logits_p = buf("h_logits", BT, lp, dtype=f32)
         L_.gemm(hh, hd["w2"], logits_p, BT, lp, Hd, bias=hd["b2"])
         sv["x_final"] = x
-        logits = logits_p[:, :nl].to(torch.float32, copy=True)
+        logits = logits_p[:, :nl].clone()
         return logits, sv
 
     # ------------------------------------------------------------------------------------------
@@ -390,7 +403,7 @@ class SwinAVEEngine:
             raise L_.StgcmaError("backward() of a stale forward: the activation arena holds one step at a time "
                                  "(run forward -> backward -> forward ...)")
         cfg, m, ar = self.cfg, self.m, self.arena
-        dev, adt, B = sv["dev"], sv["adt"], sv["B"]
+        dev, adt, sdt, B = sv["dev"], sv["adt"], sv["sdt"], sv["B"]
         fz, pk = self.frozen, self.train_pack
         fusion = sv["mode"] == "fusion"
         T = cfg.num_frames
@@ -419,22 +432,25 @@ class SwinAVEEngine:
         hd = pk["head"]
         lp, nl = hd["lp"], hd["nl"]
         Hd = hd["w0"].shape[0]
-        dlog = buf("d_logits", BT, lp, zero=True)
+        f32 = torch.float32
+        dlog = buf("d_logits", BT, lp, dtype=f32, zero=True)
         dlog[:, :nl].copy_(dlogits)
         hh, feat = slot("h_hidden"), slot("h_feat")
         L_.gemm_tn(dlog, hh, g("mlp_head.2.weight"), BT, nl, Hd, lda=lp, ldb=Hd, ldo=Hd, csumA=g("mlp_head.2.bias"))
-        dh = buf("d_hidden", BT, Hd)
+        dh = buf("d_hidden", BT, Hd, dtype=f32)
         if sv["keepmask"] is not None:
             L_.gemm(dlog, hd["w2t"], dh, BT, Hd, lp, aux=sv["keepmask"], epi=L_.EPI_MULAUX)
         else:
             L_.gemm(dlog, hd["w2t"], dh, BT, Hd, lp)
         L_.gemm_tn(dh, feat, g("mlp_head.0.weight"), BT, Hd, 2 * C, lda=Hd, ldb=2 * C, ldo=2 * C, csumA=g("mlp_head.0.bias"))
-        dfeat = buf("d_feat", BT, 2 * C)
+        dfeat = buf("d_feat", BT, 2 * C, dtype=f32)
         L_.gemm(dh, hd["w0t"], dfeat, BT, 2 * C, Hd)
-        dxn = buf(f"dA{s}", M, C)
+        dxn = buf("d_hxn", M, C, dtype=f32)
         L_.head_pool_bwd(dfeat, dxn, BT, Ls, C)
-        dx = buf(f"dB{s}", M, C)
-        L_.layernorm_bwd(dxn, sv["x_final"], slot("h_mean"), slot("h_rstd"), fz["norm"]["g"], None, dx, M, C)
+        # dx = gradient of the residual stream (stream dtype); dxb = its activation-dtype copy, written by the
+        # same kernel, which is what the GEMMs consume as an operand
+        dx, dxb = buf(f"dB{s}", M, C, dtype=sdt), buf(f"dBb{s}", M, C)
+        L_.layernorm_bwd(dxn, sv["x_final"], slot("h_mean"), slot("h_rstd"), fz["norm"]["g"], None, dx, M, C, dx_copy=dxb)
 
         def adapter_grads(prefix_names, d_out, h_in, d_hpre, x_in, M, C, r, rp, rowscale):
             """dW2/db2 from (d_out, h_in); dW1/db1 from (d_hpre, x_in), per modality."""
@@ -455,11 +471,10 @@ class SwinAVEEngine:
                 mg = fz[("merge", s)]
                 Mn = M // 4
                 dxm = buf(f"dxm{s}", Mn, 4 * C)
-                L_.gemm(dx, mg["wt"], dxm, Mn, 4 * C, 2 * C)
-                dxs = buf(f"dB{s}", M, C)
-                L_.layernorm_bwd(dxm, sv[f"m{s}_in"], slot(f"m{s}_mean"), slot(f"m{s}_rstd"), mg["g"], None, dxs, Mn, 4 * C,
-                                 merge=1, R=R)
-                dx = dxs
+                L_.gemm(dxb, mg["wt"], dxm, Mn, 4 * C, 2 * C)
+                dx, dxb = buf(f"dB{s}", M, C, dtype=sdt), buf(f"dBb{s}", M, C)
+                L_.layernorm_bwd(dxm, sv[f"m{s}_in"], slot(f"m{s}_mean"), slot(f"m{s}_rstd"), mg["g"], None, dx, Mn, 4 * C,
+                                 merge=1, R=R, dx_copy=dxb)
             for i in reversed(range(cfg.depths[s])):
                 blk = m.layers[s].blocks[i]
                 f, p = fz[(s, i)], pk[(s, i)]
@@ -478,53 +493,53 @@ class SwinAVEEngine:
                 dh2 = buf(f"dh{s}", M, rp)
                 dhpre = buf(f"dhpre{s}", M, rp)
                 if fusion:
-                    L_.gemm(dx, A["w2t"], dh2, M, rp, C, groups=2)
+                    L_.gemm(dxb, A["w2t"], dh2, M, rp, C, groups=2)
                     work = buf(f"xwork{s}", 2 * BT * Ls, dtype=torch.float32)
                     L_.xmodal_global_bwd(slot(k + "g_h"), slot(k + "g_hpre"), p["gate"], slot(k + "g_att"), slot(k + "g_lse"),
                                          dh2, dhpre, dgate2, work, BT, Ls, rp, r=r)
                     h2 = slot(k + "g_h2")
                 else:
-                    L_.gemm(dx, A["w2t"], dhpre, M, rp, C, groups=2, aux=slot(k + "g_hpre"), epi=L_.EPI_DGELU)
+                    L_.gemm(dxb, A["w2t"], dhpre, M, rp, C, groups=2, aux=slot(k + "g_hpre"), epi=L_.EPI_DGELU)
                     h2 = slot(k + "g_h")
-                adapter_grads((pfx + "S_Adapter", pfx + "S_Adapter_Audio"), dx, h2, dhpre, y, M, C, r, rp, None)
+                adapter_grads((pfx + "S_Adapter", pfx + "S_Adapter_Audio"), dxb, h2, dhpre, y, M, C, r, rp, None)
                 dy = buf(f"dA{s}", M, C)
-                L_.gemm(dhpre, A["w1t"], dy, M, C, rp, res1=dx, groups=2)
+                L_.gemm(dhpre, A["w1t"], dy, M, C, rp, res1=dxb, groups=2)
                 dfpre = buf(f"dfpre{s}", M, hid)
                 L_.gemm(dy, f["fc2_wt"], dfpre, M, hid, C, aux=slot(k + "fpre"), epi=L_.EPI_DGELU)
                 dxn = buf(f"dC{s}", M, C)
                 L_.gemm(dfpre, f["fc1_wt"], dxn, M, C, hid)
-                dx2 = buf(f"dD{s}", M, C)
-                L_.layernorm_bwd(dxn, sv[k + "x2"], slot(k + "g_mean"), slot(k + "g_rstd"), f["n2g"], dx, dx2, M, C)
+                dx2, dx2b = buf(f"dD{s}", M, C, dtype=sdt), buf(f"dDb{s}", M, C)
+                L_.layernorm_bwd(dxn, sv[k + "x2"], slot(k + "g_mean"), slot(k + "g_rstd"), f["n2g"], dx, dx2, M, C, dx_copy=dx2b)
                 # ---------------- (S) backward: dx2 ----------------
                 A = p["S2"]
                 at = slot(k + "attn")
                 if fusion:
-                    L_.gemm(dx2, A["w2t"], dh2, M, rp, C, groups=2)
+                    L_.gemm(dx2b, A["w2t"], dh2, M, rp, C, groups=2)
                     L_.xmodal_window_bwd(slot(k + "s_h"), slot(k + "s_hpre"), p["gate"], slot(k + "s_att"), dh2, dhpre, dgate2,
                                          BT, R, ws, shift, rp, r=r)
                     h2 = slot(k + "s_h2")
                 else:
-                    L_.gemm(dx2, A["w2t"], dhpre, M, rp, C, groups=2, aux=slot(k + "s_hpre"), epi=L_.EPI_DGELU)
+                    L_.gemm(dx2b, A["w2t"], dhpre, M, rp, C, groups=2, aux=slot(k + "s_hpre"), epi=L_.EPI_DGELU)
                     h2 = slot(k + "s_h")
-                adapter_grads((pfx + "S_Adapter2", pfx + "S_Adapter2_Audio"), dx2, h2, dhpre, at, M, C, r, rp, None)
+                adapter_grads((pfx + "S_Adapter2", pfx + "S_Adapter2_Audio"), dx2b, h2, dhpre, at, M, C, r, rp, None)
                 if first_block and not blk.t_attn:
                     break  # nothing upstream needs a gradient
                 dat = buf(f"dA{s}", M, C)
-                L_.gemm(dhpre, A["w1t"], dat, M, C, rp, res1=dx2, groups=2)
+                L_.gemm(dhpre, A["w1t"], dat, M, C, rp, res1=dx2b, groups=2)
                 do = buf(f"dC{s}", M, C)
                 L_.gemm(dat, f["proj_wt"], do, M, C, C)
                 dqkv = buf(f"dqkv{s}", M, 3 * C)
                 L_.window_attn_bwd(slot(k + "qkv"), f["rpb"], do, dqkv, frames2, R, ws, shift, heads)
                 dxn = buf(f"dA{s}", M, C)
                 L_.gemm(dqkv, f["qkv_wt"], dxn, M, C, 3 * C)
-                dx1 = buf(f"dB{s}", M, C)
-                L_.layernorm_bwd(dxn, sv[k + "x1"], slot(k + "s_mean"), slot(k + "s_rstd"), f["n1g"], dx2, dx1, M, C)
+                dx1, dx1b = buf(f"dB{s}", M, C, dtype=sdt), buf(f"dBb{s}", M, C)
+                L_.layernorm_bwd(dxn, sv[k + "x1"], slot(k + "s_mean"), slot(k + "s_rstd"), f["n1g"], dx2, dx1, M, C, dx_copy=dx1b)
                 # ---------------- (T) backward: dx1 ----------------
                 if blk.t_attn:
                     A = p["T"]
                     dp = sv["dp"][(s, i)]
-                    L_.gemm(dx1, A["w2t"], dhpre, M, rp, C, groups=2, rowscale=dp, aux=slot(k + "t_hpre"), epi=L_.EPI_DGELU)
-                    adapter_grads((pfx + "T_Adapter", pfx + "T_Adapter_Audio"), dx1, slot(k + "t_h"), dhpre, slot(k + "rt"),
+                    L_.gemm(dx1b, A["w2t"], dhpre, M, rp, C, groups=2, rowscale=dp, aux=slot(k + "t_hpre"), epi=L_.EPI_DGELU)
+                    adapter_grads((pfx + "T_Adapter", pfx + "T_Adapter_Audio"), dx1b, slot(k + "t_h"), dhpre, slot(k + "rt"),
                                   M, C, r, rp, dp)
                     drt = buf(f"dA{s}", M, C)
                     L_.gemm(dhpre, A["w1t"], drt, M, C, rp, groups=2)
@@ -539,11 +554,11 @@ class SwinAVEEngine:
                         break
                     dxn = buf(f"dA{s}", M, C)
                     L_.gemm(dqkv, f["qkv_wt"], dxn, M, C, 3 * C)
-                    dx0 = buf(f"dD{s}", M, C)
-                    L_.layernorm_bwd(dxn, sv[k + "x0"], slot(k + "t_mean"), slot(k + "t_rstd"), f["n1g"], dx1, dx0, M, C)
-                    dx = dx0
+                    dx0, dx0b = buf(f"dD{s}", M, C, dtype=sdt), buf(f"dDb{s}", M, C)
+                    L_.layernorm_bwd(dxn, sv[k + "x0"], slot(k + "t_mean"), slot(k + "t_rstd"), f["n1g"], dx1, dx0, M, C, dx_copy=dx0b)
+                    dx, dxb = dx0, dx0b
                 else:
-                    dx = dx1
+                    dx, dxb = dx1, dx1b
 
         out = gbuf.clone()
         if self.dp_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized() \

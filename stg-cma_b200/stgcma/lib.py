@@ -22,9 +22,9 @@ _vp, _i, _i64, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_voi
 _SIGNATURES = {
     "stgcma_check_device": [_i],
     "stgcma_patch_embed_fwd": [_fp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "stgcma_layernorm_fwd": [_vp, _fp, _fp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _vp],
-    "stgcma_layernorm_bwd": [_vp, _vp, _fp, _fp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
-    "stgcma_gemm": [_vp, _vp, _fp, _vp, _vp, _fp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _i, _vp],
+    "stgcma_layernorm_fwd": [_vp, _fp, _fp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_layernorm_bwd": [_vp, _vp, _fp, _fp, _fp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp],
+    "stgcma_gemm": [_vp, _vp, _fp, _vp, _vp, _fp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _i, _i, _vp],
     "stgcma_gemm_tn": [_vp, _vp, _fp, _fp, _fp, _fp, _i64, _i, _i, _i64, _i64, _i64, _i, _vp],
     "stgcma_window_attn_fwd": [_vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_window_attn_bwd": [_vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
@@ -168,21 +168,26 @@ def patch_embed_fwd(img, w, bias, gamma, beta, out, B, Cin, T, H, W, C):
 
 
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=0, R=0):
-    _call("stgcma_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, merge, R, dt(x),
-          cost=(0.0, 2.0 * rows * C * _es(x)))
+    _call("stgcma_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, C, merge, R, dt(x), dt(y),
+          cost=(0.0, rows * C * (_es(x) + _es(y))))
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0):
-    _call("stgcma_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), rows, C, merge, R,
-          dt(x), cost=(0.0, (3.0 + (dres is not None)) * rows * C * _es(x)))
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0, dx_copy=None):
+    _call("stgcma_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx), _p(dx_copy), rows, C,
+          merge, R, dt(dy), dt(x), dt(dx_copy if dx_copy is not None else dy),
+          cost=(0.0, rows * C * (_es(dy) + (2.0 + (dres is not None)) * _es(x) + (0 if dx_copy is None else _es(dx_copy)))))
 
 
 def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, aux=None, out_pre=None, lda=None,
          ldw=None, ldo=None, groups=1, epi=EPI_LINEAR):
+    """`out` (and `res1`, which must match it) may be fp32 while A / W are bf16: the residual stream."""
+    if res1 is not None and res1.dtype != out.dtype:
+        raise StgcmaError("gemm: res1 must have the dtype of out")
     _call("stgcma_gemm", _p(A), _p(W), _p(bias), _p(res1), _p(res2), _p(rowscale), _p(aux), _p(out), _p(out_pre), M, N,
-          K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A),
+          K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A), dt(out),
           cost=(2.0 * M * N * K, _es(A) * (M * K + groups * N * K + M * N * (
-              1.0 + (res1 is not None) + (res2 is not None) + (aux is not None) + (out_pre is not None)))))
+              0.0 + (res2 is not None) + (aux is not None) + (out_pre is not None))) + _es(out) * M * N * (
+              1.0 + (res1 is not None))))
 
 
 def gemm_tn(A, B, dW, M, Ka, Nb, *, lda, ldb, ldo, rowscale=None, csumA=None, csumB=None):

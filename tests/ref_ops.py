@@ -75,7 +75,7 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=0, R=0):
         rstd.copy_(rs)
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0, dx_copy=None):
     xr, idx = _ln_rows(_c(x), rows, C, merge, R)
     g = _c(dy).reshape(-1, C)[:rows] * _c(gamma)
     xh = (xr - _c(mean)[:, None]) * _c(rstd)[:, None]
@@ -89,6 +89,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=0, R=0):
         if dres is not None:
             d = d + _c(dres).reshape(-1, C)[:rows]
         dx.reshape(-1, C)[:rows].copy_(d)
+    if dx_copy is not None:   # the same values, rounded once to the activation dtype (GEMM operand copy)
+        dx_copy.reshape(-1).copy_(dx.reshape(-1))
 
 
 def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, aux=None, out_pre=None, lda=None,
@@ -289,8 +291,12 @@ def pack_params(table_dev, n, dtype_code):
         s = np.ctypeslib.as_array(ctypes.cast(src, ctypes.POINTER(ctypes.c_float)), shape=((rows - 1) * sld + cols,))
         sv = torch.from_numpy(np.lib.stride_tricks.as_strided(s, (rows, cols), (sld * 4, 4)).copy())
         dt_ = torch.float32 if f32 else dst_dtype
-        if dt_ == torch.bfloat16:
-            raise NotImplementedError("fake backend packs fp32 / fp64 only")
+        if dt_ == torch.bfloat16:  # numpy has no bf16: view the destination through torch
+            n_el = ((cols - 1) * dld + rows) if tr else ((rows - 1) * dld + cols)
+            d = torch.frombuffer((ctypes.c_int16 * n_el).from_address(dst), dtype=torch.bfloat16)
+            dv = torch.as_strided(d, (cols, rows) if tr else (rows, cols), (dld, 1))
+            dv.copy_(sv.t() if tr else sv)
+            continue
         ct = _CT[dt_]
         esz = ctypes.sizeof(ct)
         if tr:

@@ -71,7 +71,7 @@ def test_schedule_matches_reference_golden(monkeypatch):
     ref_ops.install_fake_backend(monkeypatch, stgcma.lib)
     fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "tiny3stage_fusion.pt"))
     cfg = O.SwinAVEConfig(**fx["cfg"])
-    sd = O.make_state(cfg, seed=fx["seed"], dtype=torch.float32)
+    sd = O.make_state(cfg, seed=fx["seed"], dtype=torch.float32, **fx["state_kw"])
     a, v, labels = O.make_inputs(cfg, fx["batch"], seed=fx["seed"])
     m = build(fx["cfg"], fx["mode"], torch.float64)
     m.train()

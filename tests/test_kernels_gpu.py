@@ -135,6 +135,51 @@ def test_layernorm(rows, C, dtype):
     assert torch.equal(dx2, dx)
 
 
+@pytest.mark.parametrize("merge", [0, 1])
+def test_layernorm_fp32_stream_bf16_activations(merge):
+    """Production layout: x / dres / dx are the fp32 residual stream, y / dy / dx_copy are bf16."""
+    frames, Rr, C4 = 3, 14, 96
+    C = 4 * C4 if merge else 192
+    rows = frames * (Rr // 2) ** 2 if merge else 500
+    xshape = (frames * Rr * Rr, C4) if merge else (rows, C)
+    x = rnd(*xshape, dtype=torch.float32, seed=1, scale=2.0) + 0.5
+    gamma, beta = rnd(C, dtype=torch.float32, seed=2) + 1.0, rnd(C, dtype=torch.float32, seed=3)
+    y = torch.empty(rows, C, dtype=torch.bfloat16, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    L().layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, merge=merge, R=Rr)
+    r_y, r_m, r_r = torch.empty(rows, C, dtype=torch.float64), torch.empty(rows, dtype=torch.float64), torch.empty(rows, dtype=torch.float64)
+    R.layernorm_fwd(cpu(x), cpu(gamma), cpu(beta), r_y, r_m, r_r, rows, C, merge=merge, R=Rr)
+    assert rel(y, r_y) < 1e-2 and rel(mean, r_m) < 1e-5 and rel(rstd, r_r) < 1e-5
+    dy = rnd(rows, C, dtype=torch.bfloat16, seed=4)
+    dres = None if merge else rnd(rows, C, dtype=torch.float32, seed=5)
+    dx, dxc = torch.full_like(x, float("nan")), torch.full(xshape, float("nan"), dtype=torch.bfloat16, device="cuda")
+    L().layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, rows, C, merge=merge, R=Rr, dx_copy=dxc)
+    r_dx = torch.empty(*xshape, dtype=torch.float64)
+    R.layernorm_bwd(cpu(dy), cpu(x), r_m, r_r, cpu(gamma), cpu(dres), r_dx, rows, C, merge=merge, R=Rr)
+    assert dx.dtype == torch.float32 and rel(dx, r_dx) < 1e-5      # fp32 stream: no bf16 rounding on it
+    assert torch.equal(dxc, dx.to(torch.bfloat16))                  # the operand copy is the same value rounded once
+    # head variant: fp32 dy as well
+    dy32 = dy.float()
+    dx2 = torch.empty_like(x)
+    L().layernorm_bwd(dy32, x, mean, rstd, gamma, dres, dx2, rows, C, merge=merge, R=Rr, dx_copy=dxc)
+    assert torch.equal(dx2, dx)
+
+
+def test_gemm_bf16_fp32_stream_epilogue():
+    """x_new(fp32) = x(fp32) + branch(bf16) + A.W^T + b : `out` / `res1` fp32, everything else bf16."""
+    M, N, K = 777, 192, 32
+    A, W = rnd(M, K, dtype=torch.bfloat16, seed=1), rnd(2, N, K, dtype=torch.bfloat16, seed=2, scale=K ** -0.5)
+    M2 = M - M % 2
+    bias = rnd(2, N, dtype=torch.float32, seed=3)
+    res1, res2 = rnd(M2, N, dtype=torch.float32, seed=4, scale=30.0), rnd(M2, N, dtype=torch.bfloat16, seed=5)
+    out = torch.full((M2, N), float("nan"), dtype=torch.float32, device="cuda")
+    L().gemm(A, W, out, M2, N, K, bias=bias, res1=res1, res2=res2, groups=2)
+    torch.cuda.synchronize()
+    ref = torch.empty(M2, N, dtype=torch.float64)
+    R.gemm(cpu(A), cpu(W), ref, M2, N, K, bias=cpu(bias), res1=cpu(res1), res2=cpu(res2), groups=2)
+    assert rel(out, ref) < 1e-5   # fp32 out: only fp32 accumulation error, no bf16 rounding of the stream
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_layernorm_patch_merge(dtype):
     frames, Rr, C4 = 3, 14, 96

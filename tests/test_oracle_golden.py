@@ -11,11 +11,11 @@ from oracle.make_goldens import probe_index
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion"])
+@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion", "swin_t_T10_B2_fusion"])
 def test_oracle_reproduces_reference(name):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     cfg = O.SwinAVEConfig(**fx["cfg"])
-    sd = O.make_state(cfg, seed=fx["seed"], dtype=torch.float64)
+    sd = O.make_state(cfg, seed=fx["seed"], dtype=torch.float64, **fx["state_kw"])
     assert list(sd.keys()) == fx["state_keys"]
     assert {k: tuple(t.shape) for k, t in sd.items()} == fx["state_shapes"]
     a, v, labels = O.make_inputs(cfg, fx["batch"], seed=fx["seed"], dtype=torch.float64)

@@ -50,19 +50,30 @@ def rel(got, ref):
 
 
 def check_grads(g, ref_g, tol, names=None):
+    """Per tensor max|got - ref| / max|ref| < tol.  The per-block gates are 1-element tensors whose gradient is
+    a full reduction <dH', attn> with heavy cancellation (some are 100x smaller than their neighbours), so a
+    per-scalar relative error is meaningless: all gates of the model are compared as ONE stacked vector."""
     bad = []
-    for n in (names or ref_g.keys()):
+    names = list(names or ref_g.keys())
+    gates = [n for n in names if "gate_" in n]
+    for n in names:
+        if n in gates:
+            continue
         e = rel(g[n], ref_g[n])
         if not e < tol:
             bad.append((n, e))
-    assert not bad, f"{len(bad)} gradient tensors beyond {tol}: {bad[:8]}"
+    if gates:
+        e = rel(torch.stack([g[n].reshape(()) for n in gates]), torch.stack([ref_g[n].reshape(()) for n in gates]))
+        if not e < tol:
+            bad.append(("gates(stacked)", e))
+    assert not bad, f"{len(bad)} gradient tensors beyond {tol}: {sorted(bad, key=lambda t: -t[1])[:8]}"
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode", ["fusion", "multimodal"])
 def test_tiny_step_vs_oracle(mode, dtype):
     cfg = O.SwinAVEConfig(**TINY)
-    sd = O.make_state(cfg, seed=3)
+    sd = O.make_state(cfg, seed=3, bf16_exact=True)   # identical weights on both sides in bf16 mode too
     a, v, labels = O.make_inputs(cfg, 2, seed=3)
     sd64 = {k: (t.double() if t.is_floating_point() else t) for k, t in sd.items()}
     r_out, r_loss, r_g = O.train_step(sd64, a.double(), v.double(), labels.double(), cfg, mode)
@@ -76,11 +87,11 @@ def test_tiny_step_vs_oracle(mode, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion"])
+@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion", "swin_t_T10_B2_fusion"])
 def test_step_vs_reference_golden(name, dtype):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     cfg = O.SwinAVEConfig(**fx["cfg"])
-    sd = O.make_state(cfg, seed=fx["seed"])
+    sd = O.make_state(cfg, seed=fx["seed"], **fx["state_kw"])
     a, v, labels = O.make_inputs(cfg, fx["batch"], seed=fx["seed"])
     m = build(fx["cfg"], fx["mode"], dtype, sd)
     out, loss, g = step(m, a, v, labels, fx["mode"])
