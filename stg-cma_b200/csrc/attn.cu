@@ -287,6 +287,12 @@ __global__ void __launch_bounds__(128) temporal_attn_bwd_kernel(const T* __restr
   if (threadIdx.x < 2 * Tn - 1) atomicAdd(dtbl + ((int64_t)g * (2 * Tn - 1) + threadIdx.x) * heads + h, dbias[threadIdx.x]);
 }
 
+// bf16 production kernels (tensor cores), attn_tc.cu
+int window_attn_fwd_bf16(const void* qkv, const float* rpb, void* out, int64_t frames, int R, int ws, int shift, int heads,
+                         cudaStream_t st);
+int window_attn_bwd_bf16(const void* qkv, const float* rpb, const void* dout, void* dqkv, int64_t frames, int R, int ws,
+                         int shift, int heads, cudaStream_t st);
+
 }  // namespace stgcma
 
 using namespace stgcma;
@@ -310,7 +316,7 @@ extern "C" int stgcma_window_attn_fwd(const void* qkv, const float* rpb, void* o
   if (dtype == STGCMA_F32)
     window_attn_fwd_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, rpb, (float*)out, R, ws, shift, heads);
   else if (dtype == STGCMA_BF16)
-    window_attn_fwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)qkv, rpb, (bf16*)out, R, ws, shift, heads);
+    return window_attn_fwd_bf16(qkv, rpb, out, frames, R, ws, shift, heads, st);
   else
     STG_REQUIRE(false, "window_attn_fwd: bad dtype %d", dtype);
   return check_launch("window_attn_fwd");
@@ -325,7 +331,7 @@ extern "C" int stgcma_window_attn_bwd(const void* qkv, const float* rpb, const v
   if (dtype == STGCMA_F32)
     window_attn_bwd_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, rpb, (const float*)dout, (float*)dqkv, R, ws, shift, heads);
   else if (dtype == STGCMA_BF16)
-    window_attn_bwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)qkv, rpb, (const bf16*)dout, (bf16*)dqkv, R, ws, shift, heads);
+    return window_attn_bwd_bf16(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads, st);
   else
     STG_REQUIRE(false, "window_attn_bwd: bad dtype %d", dtype);
   return check_launch("window_attn_bwd");

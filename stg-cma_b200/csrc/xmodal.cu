@@ -465,6 +465,12 @@ static int xg_bwd_launch(const void* h, const void* hpre, const float* gate, con
     default: rc = -1;                               \
   }
 
+// bf16 production kernels (tensor cores), xmodal_tc.cu
+int xmodal_global_fwd_bf16(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L,
+                           int rp, cudaStream_t st);
+int xmodal_global_bwd_bf16(const void* h, const void* hpre, const float* gate, const float* lse, const float* D,
+                           const void* dout, void* dh, int64_t frames, int L, int rp, cudaStream_t st);
+
 }  // namespace stgcma
 
 using namespace stgcma;
@@ -537,7 +543,7 @@ extern "C" int stgcma_xmodal_global_fwd(const void* h, const float* gate, void* 
   if (dtype == STGCMA_F32) {
     XG_DISPATCH_RP(rp, rc = (xg_fwd_launch<float, RP_>(h, gate, out, attn_out, lse, frames, L, st)));
   } else if (dtype == STGCMA_BF16) {
-    XG_DISPATCH_RP(rp, rc = (xg_fwd_launch<bf16, RP_>(h, gate, out, attn_out, lse, frames, L, st)));
+    rc = xmodal_global_fwd_bf16(h, gate, out, attn_out, lse, frames, L, rp, st);
   } else {
     STG_REQUIRE(false, "xmodal_global_fwd: bad dtype %d", dtype);
   }
@@ -565,7 +571,7 @@ extern "C" int stgcma_xmodal_global_bwd(const void* h, const void* hpre, const f
     xmodal_prep_kernel<bf16><<<pgrid, 256, 0, st>>>((const bf16*)dout, (const bf16*)attn_out, gate, work, dgate, rows, rp);
     rc = check_launch("xmodal_prep");
     if (rc) return rc;
-    XG_DISPATCH_RP(rp, rc = (xg_bwd_launch<bf16, RP_>(h, hpre, gate, lse, work, dout, dh, frames, L, st)));
+    rc = xmodal_global_bwd_bf16(h, hpre, gate, lse, work, dout, dh, frames, L, rp, st);
   } else {
     STG_REQUIRE(false, "xmodal_global_bwd: bad dtype %d", dtype);
   }
