@@ -98,6 +98,33 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// bf16 production path: erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 round-off level; GELU and
+// GELU' below are within 7e-7 absolute of the erff versions over [-8, 8]) at about half the instructions of erff:
+// one MUFU.RCP, one MUFU.EX2 and 8 FMAs, and the exponential is shared with the Gaussian term of the gradient.
+// The fp32 check mode keeps erff.
+__device__ __forceinline__ void erf_exp_fast(float x, float& erf_z, float& exp_mz2) {   // z = x / sqrt(2)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  exp_mz2 = __expf(-z * z);
+  const float e = fmaf(-p * t, exp_mz2, 1.0f);
+  erf_z = copysignf(e, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e, g;
+  erf_exp_fast(x, e, g);
+  return 0.5f * x * (1.0f + e);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float e, g;
+  erf_exp_fast(x, e, g);
+  return fmaf(x * 0.39894228040143268f, g, 0.5f * (1.0f + e));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -4,8 +4,8 @@
 //       bf16: persistent warp-specialised tcgen05 kernel -- TMA (SWIZZLE_128B, 3-D maps so the
 //             per-modality "groups" never bleed into each other) -> 128 x BN x 64 smem stages ->
 //             tcgen05.mma (cta_group::1, M=128, fp32 accumulators double-buffered in TMEM) ->
-//             4 epilogue warps: tcgen05.ld -> bias -> smem transpose -> coalesced 128-bit
-//             residual / GELU / dGELU epilogue.
+//             8 epilogue warps: operand loads issued first, tcgen05.ld -> smem transpose -> bias ->
+//             residual / GELU / dGELU / row-scale -> coalesced 128-bit stores.
 //       fp32: plain CUDA-core tiled GEMM (the check mode; also the numerics reference).
 //   stgcma_gemm_tn   dW += A^T . B   (trainable adapter / head weights), split over rows,
 //                    fp32 atomics into the gradient bucket.
@@ -44,54 +44,96 @@ __device__ __forceinline__ void epi_elem(const EpiParams& p, int64_t row, int co
   }
 }
 
-// 8 consecutive columns of one row, 128-bit accesses.  Activation tensors (res2 / aux / out_pre) are bf16;
-// `out` and `res1` are bf16, or fp32 when p.out_f32 (the residual stream).
-__device__ __forceinline__ void epi_vec8(const EpiParams& p, int64_t row, int col, float (&v)[8]) {
-  const int64_t off = row * p.ldo + col;
-  float o[8];
+// Epilogue of the tcgen05 kernel.  An epilogue warp owns 32 rows x 32 columns per step.  The 32x32b TMEM load
+// hands every lane 32 columns of ITS OWN row; accessing global memory that way would touch 32 cache lines per
+// warp instruction (measured: the LSU wavefront rate then caps the kernel at ~2 TB/s), so the chunk is
+// transposed through a padded shared-memory staging tile into a coalesced layout -- 4 lanes x 8 columns per
+// row, 8 rows per pass, 4 passes -- in which every residual / aux load and every store is a 128-bit access
+// and a warp instruction covers 64..128 contiguous bytes per row.  All operand loads of a chunk are issued
+// first (`epi_load`: before the TMEM read, and for the first chunk of a tile before the accumulator is even
+// ready) and consumed afterwards (`epi_apply`); the epilogue is latency-bound otherwise.
+// Activation tensors (res2 / aux / out_pre) are bf16; `out` and `res1` are bf16, or fp32 when p.out_f32.
+// The epilogue variant is a compile-time property of the kernel (MODE, OUT_F32, NRES = number of residual
+// operands): with run-time flags the chunk loop executed ~400 instructions per 32 x 32 chunk, 80 % of them
+// uniform branches and constant-bank loads (ncu source page, profiles/r01b), and was issue-bound.
+struct EpiRegs {
+  uint4 a[4][2];  // per pass: res1 (fp32: 2 x 16 B, bf16: 1 x 16 B)  or aux (bf16)
+  uint4 b[4];     // per pass: res2 (bf16)
+  float rs[4];    // per pass: rowscale
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// off0: element offset (row * ldo + col) of this lane in pass 0; pass ps is pass_stride elements further.
+template <int MODE, bool OUT_F32, int NRES>
+__device__ __forceinline__ void epi_load(const EpiParams& p, int64_t off0, int64_t pass_stride, int64_t row0, int rpp,
+                                         int nvalid, EpiRegs& r) {
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    if (ps >= nvalid) continue;
+    const int64_t off = off0 + ps * pass_stride;
+    r.rs[ps] = p.rowscale ? __ldg(p.rowscale + row0 + ps * rpp) : 1.f;
+    if (MODE == STGCMA_EPI_LINEAR) {
+      if (NRES >= 1) {
+        if (OUT_F32) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res1) + off);
+          r.a[ps][0] = s4[0];
+          r.a[ps][1] = s4[1];
+        } else {
+          r.a[ps][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res1) + off);
+        }
+      }
+      if (NRES >= 2) r.b[ps] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res2) + off);
+    } else if (MODE != STGCMA_EPI_GELU) {
+      r.a[ps][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + off);
+    }
+  }
+}
+
+// v: acc + bias of 8 consecutive columns of one row (pass ps of the chunk)
+template <int MODE, bool OUT_F32, int NRES>
+__device__ __forceinline__ void epi_apply(const EpiParams& p, int64_t off, int ps, float (&v)[8], const EpiRegs& r) {
   if (p.rowscale) {
-    const float s = p.rowscale[row];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= s;
+    for (int i = 0; i < 8; ++i) v[i] *= r.rs[ps];
   }
-  switch (p.mode) {
-    case STGCMA_EPI_LINEAR: {
-      if (p.res1) {
-        float r[8];
-        if (p.out_f32) load8(reinterpret_cast<const float*>(p.res1) + off, r);
-        else load8(reinterpret_cast<const bf16*>(p.res1) + off, r);
+  if (MODE == STGCMA_EPI_LINEAR) {
+    if (NRES >= 1) {
+      if (OUT_F32) {
+        const float4 x = *reinterpret_cast<const float4*>(&r.a[ps][0]), y = *reinterpret_cast<const float4*>(&r.a[ps][1]);
+        v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+      } else {
+        float t[8];
+        unpack8(r.a[ps][0], t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
+        for (int i = 0; i < 8; ++i) v[i] += t[i];
       }
-      if (p.res2) {
-        float r[8];
-        load8(reinterpret_cast<const bf16*>(p.res2) + off, r);
+    }
+    if (NRES >= 2) {
+      float t[8];
+      unpack8(r.b[ps], t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
-      }
+      for (int i = 0; i < 8; ++i) v[i] += t[i];
+    }
+  } else if (MODE == STGCMA_EPI_GELU) {
+    if (p.out_pre) store8(reinterpret_cast<bf16*>(p.out_pre) + off, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = v[i];
-    } break;
-    case STGCMA_EPI_GELU: {
-      if (p.out_pre) store8(reinterpret_cast<bf16*>(p.out_pre) + off, v);
+    for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+  } else {
+    float t[8];
+    unpack8(r.a[ps][0], t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = gelu_erf(v[i]);
-    } break;
-    case STGCMA_EPI_DGELU: {
-      float a[8];
-      load8(reinterpret_cast<const bf16*>(p.aux) + off, a);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = v[i] * gelu_erf_grad(a[i]);
-    } break;
-    default: {
-      float a[8];
-      load8(reinterpret_cast<const bf16*>(p.aux) + off, a);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = v[i] * a[i];
-    } break;
+    for (int i = 0; i < 8; ++i) v[i] *= (MODE == STGCMA_EPI_DGELU) ? gelu_grad_fast(t[i]) : t[i];
   }
-  if (p.out_f32) store8(reinterpret_cast<float*>(p.out) + off, o);
-  else store8(reinterpret_cast<bf16*>(p.out) + off, o);
+  if (OUT_F32) store8(reinterpret_cast<float*>(p.out) + off, v);
+  else store8(reinterpret_cast<bf16*>(p.out) + off, v);
 }
 
 // =========================================================================================
@@ -155,9 +197,10 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
-constexpr int kStageRowF = 36;           // staging row stride in floats (32 + 4 pad, keeps 16 B alignment)
-constexpr int kStagingBytes = 4 * 32 * kStageRowF * 4;
+constexpr int kEpiWarps = 8;             // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int kThreads = 64 + kEpiWarps * 32;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
+constexpr int kStageRowF = 36;           // staging row stride in floats (32 + 4 pad: conflict-free 128-bit rows)
+constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowF * 4;
 constexpr int kABytes = BM * BK * 2;     // 16 KiB
 
 struct Params {
@@ -268,10 +311,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// OCC: CTAs per SM the variant is compiled for.  OCC = 2 (BN <= 128, half the smem / TMEM each) is used for the
+// small-K, epilogue-bound shapes: two tiles in flight per SM hide the epilogue latency; OCC = 1 (BN <= 256) for the
+// large-K, tensor-bound ones (a 128 x 256 tile reads 25 % less shared memory per flop than two 128 x 128 tiles).
+template <int MODE, bool OUT_F32, int NRES, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024 B alignment for SWIZZLE_128B, by pointer arithmetic on the shared pointer (keeps ld/st.shared addressing)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t stage_bytes = kABytes + (uint32_t)p.BN * 128u;
   float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + kStagingBytes);
@@ -292,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(tfull + s), 1);
-      mbar_init(smem_u32(tempty + s), 4);
+      mbar_init(smem_u32(tempty + s), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -359,57 +407,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM -> regs -> smem -> global) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (TMEM -> regs -> smem transpose -> global) =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int par = (warp - 2) >> 2;    // 0: even 32-column chunks, 1: odd chunks
+    const int nchunks = (p.BN + 31) >> 5;
     float* stg = staging + (size_t)(warp - 2) * 32 * kStageRowF;
+    const EpiParams ep = p.epi;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
       const int g = mt / p.m_tiles_g;
       const int m_blk = mt - g * p.m_tiles_g;
-      mbar_wait(smem_u32(tfull + acc), acc_phase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + acc * (uint32_t)p.BN + ((uint32_t)(q * 32) << 16);
-      const int64_t row_base = (int64_t)m_blk * BM + q * 32;  // first row (within the group) of this warp
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        const int wc = (p.BN - c0 >= 32) ? 32 : 16;
+      const int64_t wrow = (int64_t)m_blk * BM + q * 32;   // first row (within the group) of this warp
+      bool waited = false;
+      for (int ch = par; ch < nchunks; ch += 2) {
+        const int c0 = ch << 5;
+        const bool wide = p.BN - c0 >= 32;
+        const int lpr = wide ? 4 : 2;       // lanes per row (8 columns each)
+        const int rpp = wide ? 8 : 16;      // rows per pass
+        const int r_in = wide ? (lane >> 2) : (lane >> 1), seg = wide ? (lane & 3) : (lane & 1);
+        const int col = n_blk * p.BN + c0 + seg * 8;
+        const bool col_ok = col < p.N;
+        // passes whose row is inside the group: rows wrow + r_in + ps * rpp, ps < (wide ? 4 : 2)
+        const int64_t rows_left = p.group_rows - (wrow + r_in);
+        int nvalid = rows_left <= 0 ? 0 : (int)((rows_left + rpp - 1) / rpp);
+        nvalid = nvalid > 32 / rpp ? 32 / rpp : nvalid;
+        if (!col_ok) nvalid = 0;
+        const int64_t grow0 = (int64_t)g * p.group_rows + wrow + r_in;
+        const int64_t off0 = grow0 * ep.ldo + col;
+        const int64_t pstride = (int64_t)rpp * ep.ldo;
+        EpiRegs er;
+        epi_load<MODE, OUT_F32, NRES>(ep, off0, pstride, grow0, rpp, nvalid, er);
+        float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (ep.bias && nvalid > 0) load8(ep.bias + (int64_t)g * p.N + col, bias8);
+        if (!waited) {
+          mbar_wait(smem_u32(tfull + acc), acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
         float v[32];
-        if (wc == 32) tmem_ld32(t_row + (uint32_t)c0, v);
+        if (wide) tmem_ld32(t_row + (uint32_t)c0, v);
         else tmem_ld16(t_row + (uint32_t)c0, v);
-        if (c0 + wc >= p.BN) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+        if (ch + 2 >= nchunks) {
+          // all TMEM reads of this warp for this accumulator are done: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(tempty + acc));
         }
-        const int ncol0 = n_blk * p.BN + c0;
-        if (p.epi.bias) {
-          const float* b = p.epi.bias + (int64_t)g * p.N + ncol0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < wc && ncol0 + j < p.N) v[j] += __ldg(b + j);
-        }
         float4* srow = reinterpret_cast<float4*>(stg + lane * kStageRowF);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j * 4 < wc) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (j < 4 || wide) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        const int lpr = wc >> 3;            // lanes per row (8 columns each)
-        const int rpp = 32 / lpr;           // rows per pass
-        const int r_in = lane / lpr, seg = lane - r_in * lpr;
-        for (int r0 = 0; r0 < 32; r0 += rpp) {
-          const int rl = r0 + r_in;
-          const int64_t row = row_base + rl;
-          const int col = ncol0 + seg * 8;
-          if (row < p.group_rows && col < p.N) {
-            const float4* s4 = reinterpret_cast<const float4*>(stg + rl * kStageRowF + seg * 8);
-            const float4 a = s4[0], b = s4[1];
-            float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            epi_vec8(p.epi, (int64_t)g * p.group_rows + row, col, o);
+        if (nvalid > 0) {
+          const float* sbase = stg + r_in * kStageRowF + seg * 8;
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            if (ps >= nvalid) continue;
+            const float4* s4 = reinterpret_cast<const float4*>(sbase + ps * rpp * kStageRowF);
+            const float4 x = s4[0], y = s4[1];
+            float o[8] = {x.x + bias8[0], x.y + bias8[1], x.z + bias8[2], x.w + bias8[3],
+                          y.x + bias8[4], y.y + bias8[5], y.z + bias8[6], y.w + bias8[7]};
+            epi_apply<MODE, OUT_F32, NRES>(ep, off0 + ps * pstride, ps, o, er);
           }
         }
         __syncwarp();
+      }
+      if (!waited) {
+        // this warp owns no chunk of the tile (BN <= 32 and par == 1): it still takes part in the handshake
+        mbar_wait(smem_u32(tfull + acc), acc_phase);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty + acc));
       }
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
@@ -471,8 +541,16 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   p.N = N;
   p.K = K;
   p.groups = groups;
-  const int nt = (int)ceil_div(N, 256);
-  p.BN = (int)ceil_div(ceil_div(N, nt), 16) * 16;
+  // tile width: the multiple of 16 (<= bn_max) that wastes the fewest padded columns, larger on ties
+  const int occ = (K >= 1024) ? 1 : 2;
+  const int bn_max = occ == 1 ? 256 : 128;
+  int best_bn = 16;
+  int64_t best_cost = -1;
+  for (int bn = bn_max; bn >= 16; bn -= 16) {
+    const int64_t cost = ceil_div(N, bn) * (int64_t)bn + (bn < 64 && N > bn ? N : 0);   // avoid slivers when N is large
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+  }
+  p.BN = best_bn;
   p.n_tiles = (int)ceil_div(N, p.BN);
   p.m_tiles_g = (int)ceil_div(p.group_rows, BM);
   const int64_t tiles = (int64_t)groups * p.m_tiles_g * p.n_tiles;
@@ -480,7 +558,8 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   p.num_tiles = (int)tiles;
   p.k_blocks = (int)ceil_div(K, BK);
   const int stage_bytes = kABytes + p.BN * 128;
-  const int budget = 232448 - 1024 - kStagingBytes - 256;
+  const int smem_cap = occ == 1 ? 232448 : (233472 / 2 - 1024);   // per CTA; 1 KB per CTA is reserved by the driver
+  const int budget = smem_cap - 1024 - kStagingBytes - 256;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
@@ -497,18 +576,54 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   if (rc) return rc;
 
   const size_t smem = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 256;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-  });
-  if (attr_err != cudaSuccess) {
-    set_error("gemm: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));
-    return STGCMA_ECUDA;
+  const int grid = p.num_tiles < occ * sm_count() ? p.num_tiles : occ * sm_count();
+  const int nres = (ep.mode == STGCMA_EPI_LINEAR) ? (ep.res1 ? (ep.res2 ? 2 : 1) : 0) : 0;
+  if (ep.mode == STGCMA_EPI_LINEAR && ep.res2 && !ep.res1) {
+    set_error("gemm(bf16): res2 without res1 is not supported");
+    return STGCMA_EINVAL;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  gemm_tc_kernel<<<grid, kThreads, smem, st>>>(tmA, tmW, p);
-  return check_launch("gemm(tcgen05)");
+#define STG_TC_LAUNCH(MODE_, F32_, NRES_)                                                                      \
+  do {                                                                                                         \
+    if (occ == 1) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 1);                                                       \
+    STG_TC_LAUNCH2(MODE_, F32_, NRES_, 2);                                                                     \
+  } while (0)
+#define STG_TC_LAUNCH2(MODE_, F32_, NRES_, OCC_)                                                               \
+  do {                                                                                                         \
+    auto kern = gemm_tc_kernel<MODE_, F32_, NRES_, OCC_>;                                                      \
+    static std::once_flag once;                                                                                \
+    static cudaError_t attr_err = cudaSuccess;                                                                 \
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCC_ == 1 ? 232448 : 115712); }); \
+    if (attr_err != cudaSuccess) {                                                                             \
+      set_error("gemm: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));                    \
+      return STGCMA_ECUDA;                                                                                     \
+    }                                                                                                          \
+    kern<<<grid, kThreads, smem, st>>>(tmA, tmW, p);                                                           \
+    return check_launch("gemm(tcgen05)");                                                                      \
+  } while (0)
+  const bool f32 = ep.out_f32 != 0;
+  switch (ep.mode) {
+    case STGCMA_EPI_LINEAR:
+      if (f32) {
+        if (nres == 0) STG_TC_LAUNCH(STGCMA_EPI_LINEAR, true, 0);
+        if (nres == 1) STG_TC_LAUNCH(STGCMA_EPI_LINEAR, true, 1);
+        STG_TC_LAUNCH(STGCMA_EPI_LINEAR, true, 2);
+      } else {
+        if (nres == 0) STG_TC_LAUNCH(STGCMA_EPI_LINEAR, false, 0);
+        if (nres == 1) STG_TC_LAUNCH(STGCMA_EPI_LINEAR, false, 1);
+        STG_TC_LAUNCH(STGCMA_EPI_LINEAR, false, 2);
+      }
+    case STGCMA_EPI_GELU:
+      if (f32) STG_TC_LAUNCH(STGCMA_EPI_GELU, true, 0);
+      STG_TC_LAUNCH(STGCMA_EPI_GELU, false, 0);
+    case STGCMA_EPI_DGELU:
+      if (f32) STG_TC_LAUNCH(STGCMA_EPI_DGELU, true, 0);
+      STG_TC_LAUNCH(STGCMA_EPI_DGELU, false, 0);
+    default:
+      if (f32) STG_TC_LAUNCH(STGCMA_EPI_MULAUX, true, 0);
+      STG_TC_LAUNCH(STGCMA_EPI_MULAUX, false, 0);
+  }
+#undef STG_TC_LAUNCH
+#undef STG_TC_LAUNCH2
 }
 
 }  // namespace tc
@@ -601,6 +716,10 @@ static int gemm_tn_launch(const void* A, const void* B, const float* rowscale, f
   return check_launch("gemm_tn");
 }
 
+// bf16 tensor-core version (gemm_tn_tc.cu); -1 = arguments do not fit it
+int gemm_tn_bf16(const void* A, const void* B, float* dW, float* csumA, int64_t M, int Ka, int Nb, int64_t lda, int64_t ldb,
+                 int64_t ldo, cudaStream_t st);
+
 }  // namespace stgcma
 
 using namespace stgcma;
@@ -632,7 +751,7 @@ extern "C" int stgcma_gemm(const void* A, const void* W, const float* bias, cons
   STG_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "gemm(bf16): N=%d ldo=%lld must be multiples of 8", N, (long long)ldo);
   STG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
                   ((uintptr_t)res1 & 15) == 0 && ((uintptr_t)res2 & 15) == 0 && ((uintptr_t)aux & 15) == 0 &&
-                  ((uintptr_t)out_pre & 15) == 0,
+                  ((uintptr_t)out_pre & 15) == 0 && ((uintptr_t)bias & 15) == 0,
               "gemm(bf16): operands must be 16-byte aligned");
   return tc::launch(A, W, M, N, K, lda, ldw, groups, ep, st);
 }
@@ -643,6 +762,12 @@ extern "C" int stgcma_gemm_tn(const void* A, const void* B, const float* rowscal
   STG_REQUIRE(A && B && dW, "gemm_tn: null operand");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == STGCMA_F32) return gemm_tn_launch<float>(A, B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb, ldo, st);
-  if (dtype == STGCMA_BF16) return gemm_tn_launch<bf16>(A, B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb, ldo, st);
+  if (dtype == STGCMA_BF16) {
+    if (!rowscale && !csumB) {
+      const int rc = gemm_tn_bf16(A, B, dW, csumA, M, Ka, Nb, lda, ldb, ldo, st);
+      if (rc != -1) return rc;
+    }
+    return gemm_tn_launch<bf16>(A, B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb, ldo, st);
+  }
   STG_REQUIRE(false, "gemm_tn: bad dtype %d", dtype);
 }

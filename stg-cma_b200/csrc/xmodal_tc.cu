@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
       const int64_t o = off_own + (int64_t)r * RP + col;
       if (hpre) {
         const __nv_bfloat162 hp = *reinterpret_cast<const __nv_bfloat162*>(hpre + o);
-        v0 *= gelu_erf_grad(__bfloat162float(hp.x));
-        v1 *= gelu_erf_grad(__bfloat162float(hp.y));
+        v0 *= gelu_grad_fast(__bfloat162float(hp.x));
+        v1 *= gelu_grad_fast(__bfloat162float(hp.y));
       }
       *reinterpret_cast<uint32_t*>(dh + o) = pack_bf16(v0, v1);
     }

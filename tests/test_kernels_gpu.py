@@ -95,21 +95,30 @@ def test_gemm_bf16_padded_strides():
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("M,Ka,lda,Nb,ldb,rs", [(5000, 16, 16, 96, 96, False), (333, 96, 96, 12, 16, True),
-                                               (20, 29, 32, 512, 512, False), (70000, 48, 48, 768, 768, False)])
-def test_gemm_tn(M, Ka, lda, Nb, ldb, rs, dtype):
+@pytest.mark.parametrize("M,Ka,lda,Nb,ldb,rs,colsum_b", [
+    (5000, 16, 16, 96, 96, False, True), (333, 96, 96, 12, 16, True, True), (20, 29, 32, 512, 512, False, True),
+    (70000, 48, 48, 768, 768, False, True),
+    # the engine's calls (no rowscale, no csumB): the bf16 tensor-core kernel
+    (50176, 96, 96, 12, 16, False, False), (50176, 12, 16, 96, 96, False, False), (3137, 384, 384, 24, 32, False, False),
+    (3137, 24, 32, 384, 384, False, False), (999, 768, 768, 48, 48, False, False), (999, 48, 48, 768, 768, False, False),
+    (100, 29, 32, 512, 512, False, False), (70, 192, 192, 24, 32, False, False)])
+def test_gemm_tn(M, Ka, lda, Nb, ldb, rs, colsum_b, dtype):
     A = rnd(M, lda, dtype=dtype, seed=1)
     B = rnd(M, ldb, dtype=dtype, seed=2)
+    A[:, Ka:] = 0   # pad columns of the engine's tensors are zero
+    B[:, Nb:] = 0
     rowscale = (torch.rand(M, generator=torch.Generator().manual_seed(3)) * 2).cuda() if rs else None
     dW = torch.zeros(Ka, Nb, device="cuda")
     ca = torch.zeros(Ka, device="cuda")
-    cb = torch.zeros(Nb, device="cuda")
+    cb = torch.zeros(Nb, device="cuda") if colsum_b else None
     L().gemm_tn(A, B, dW, M, Ka, Nb, lda=lda, ldb=ldb, ldo=Nb, rowscale=rowscale, csumA=ca, csumB=cb)
     torch.cuda.synchronize()
     r_dW, r_ca, r_cb = torch.zeros(Ka, Nb, dtype=torch.float64), torch.zeros(Ka, dtype=torch.float64), torch.zeros(Nb, dtype=torch.float64)
     R.gemm_tn(cpu(A), cpu(B), r_dW, M, Ka, Nb, lda=lda, ldb=ldb, ldo=Nb, rowscale=cpu(rowscale), csumA=r_ca, csumB=r_cb)
     tol = 1e-4  # fp32 accumulation of exactly-represented inputs in both modes
-    assert rel(dW, r_dW) < tol and rel(ca, r_ca) < tol and rel(cb, r_cb) < tol
+    assert rel(dW, r_dW) < tol and rel(ca, r_ca) < tol
+    if colsum_b:
+        assert rel(cb, r_cb) < tol
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
