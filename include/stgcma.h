@@ -95,6 +95,26 @@ int stgcma_gemm(const void* A, const void* W, const float* bias, const void* res
                 int64_t lda, int64_t ldw, int64_t ldo, int groups, int epilogue, int dtype, int out_dtype,
                 void* stream);
 
+/* ---- fused frozen MLP of the (G) sub-block, bf16 production mode only (Swin_AVE.py:790-797) ------
+ * fwd:  xn = LayerNorm(x; gamma, beta)  (norm2 :353)         x: fp32 residual stream [M, C]
+ *       y  = fc2(GELU(fc1(xn)))         (Mlp.forward :121-127) W1 [H, C], b1 [H], W2 [C, H], b2 [C]
+ *       hpre = y Wa[g]^T + ba[g], h = GELU(hpre)  (S_Adapter[_Audio].D_fc1 + act :796-797)  Wa [groups, rp, C]
+ *       The H-wide hidden activation never leaves the SM (chained tcgen05 GEMMs through TMEM / shared memory).
+ *       Writes y [M, C], hpre, h [M, rp] (activation dtype) and mean, rstd fp32 [M] (saved for backward).
+ * bwd:  dxn = [ ((dhpre Wa[g] + dxb) W2) * gelu'(xn W1^T + b1) ] W1      -- gradient wrt xn = LN2(x), [M, C]
+ *       (the hidden pre-activation is recomputed from x and the saved statistics; nothing H-wide is stored).
+ *       dhpre [M, rp]: gradient wrt hpre; dxb [M, C]: gradient wrt y coming from the residual (activation dtype).
+ *       Wat [groups, C, rp] = Wa transposed, W2t [H, C] = W2 transposed, W1t [C, H] = W1 transposed.
+ * Limits: C % 32 == 0, C <= 384 (fwd) / 256 (bwd); H % 64 == 0; rp % 16 == 0, rp <= 128; all pointers 16-byte
+ * aligned.  Returns STGCMA_EINVAL outside them (the caller then composes layernorm + gemm).       */
+int stgcma_mlp_fwd(const float* x, const float* gamma, const float* beta, const void* W1, const float* b1,
+                   const void* W2, const float* b2, const void* Wa, const float* ba, void* y, void* hpre, void* h,
+                   float* mean, float* rstd, int64_t M, int C, int H, int rp, int groups, int dtype, void* stream);
+int stgcma_mlp_bwd(const void* dhpre, const void* dxb, const float* x, const float* gamma, const float* beta,
+                   const float* mean, const float* rstd, const void* Wat, const void* W1, const float* b1,
+                   const void* W2t, const void* W1t, void* dxn, int64_t M, int C, int H, int rp, int groups,
+                   int dtype, void* stream);
+
 /* ---- weight gradients of the trainable nn.Linear layers (adapters, head) -------------------
  * dW[i, j] += sum_m rowscale[m] * A[m, i] * B[m, j]   (i < Ka, j < Nb; dW fp32, row stride ldo)
  * csumA[i] += sum_m rowscale[m] * A[m, i]  (when non-NULL);  csumB likewise.  Accumulates

@@ -334,17 +334,22 @@ class SwinAVEEngine:
                 sv[k + "x1"] = x
                 x = x2
                 # ---------------- (G) frozen MLP + global cross-modal adapter ----------------
-                xn = buf(f"xn{s}", M, C)
                 mean, rstd = buf(k + "g_mean", M, dtype=torch.float32), buf(k + "g_rstd", M, dtype=torch.float32)
-                L_.layernorm_fwd(x, f["n2g"], f["n2b"], xn, mean, rstd, M, C)
                 hid = f["fc1_w"].shape[0]
-                fpre, fact = buf(k + "fpre", M, hid), buf(f"fact{s}", M, hid)
-                L_.gemm(xn, f["fc1_w"], fact, M, hid, C, bias=f["fc1_b"], out_pre=fpre, epi=L_.EPI_GELU)
                 y = buf(k + "y", M, C)
-                L_.gemm(fact, f["fc2_w"], y, M, C, hid, bias=f["fc2_b"])
                 hpre, h = buf(k + "g_hpre", M, rp), buf(k + "g_h", M, rp)
                 A = p["S"]
-                L_.gemm(y, A["w1"], h, M, rp, C, bias=A["b1"], out_pre=hpre, groups=2, epi=L_.EPI_GELU)
+                if L_.mlp_fused_ok(C, hid, rp, adt):
+                    # one kernel: LN2 -> fc1 -> GELU -> fc2 -> adapter fc1 (+GELU); the 4C-wide hidden stays on chip
+                    L_.mlp_fwd(x, f["n2g"], f["n2b"], f["fc1_w"], f["fc1_b"], f["fc2_w"], f["fc2_b"], A["w1"], A["b1"], y,
+                               hpre, h, mean, rstd, M, C, hid, rp)
+                else:
+                    xn = buf(f"xn{s}", M, C)
+                    L_.layernorm_fwd(x, f["n2g"], f["n2b"], xn, mean, rstd, M, C)
+                    fpre, fact = buf(k + "fpre", M, hid), buf(f"fact{s}", M, hid)
+                    L_.gemm(xn, f["fc1_w"], fact, M, hid, C, bias=f["fc1_b"], out_pre=fpre, epi=L_.EPI_GELU)
+                    L_.gemm(fact, f["fc2_w"], y, M, C, hid, bias=f["fc2_b"])
+                    L_.gemm(y, A["w1"], h, M, rp, C, bias=A["b1"], out_pre=hpre, groups=2, epi=L_.EPI_GELU)
                 if fusion:
                     h2, att = buf(k + "g_h2", M, rp), buf(k + "g_att", M, rp)
                     lse = buf(k + "g_lse", 2 * BT * Ls, dtype=torch.float32)
@@ -502,12 +507,17 @@ class SwinAVEEngine:
                     L_.gemm(dxb, A["w2t"], dhpre, M, rp, C, groups=2, aux=slot(k + "g_hpre"), epi=L_.EPI_DGELU)
                     h2 = slot(k + "g_h")
                 adapter_grads((pfx + "S_Adapter", pfx + "S_Adapter_Audio"), dxb, h2, dhpre, y, M, C, r, rp, None)
-                dy = buf(f"dA{s}", M, C)
-                L_.gemm(dhpre, A["w1t"], dy, M, C, rp, res1=dxb, groups=2)
-                dfpre = buf(f"dfpre{s}", M, hid)
-                L_.gemm(dy, f["fc2_wt"], dfpre, M, hid, C, aux=slot(k + "fpre"), epi=L_.EPI_DGELU)
                 dxn = buf(f"dC{s}", M, C)
-                L_.gemm(dfpre, f["fc1_wt"], dxn, M, C, hid)
+                if L_.mlp_fused_ok(C, hid, rp, adt):
+                    # one kernel: dy = dhpre W1a + dxb -> (dy W2) * gelu'(recomputed fc1(LN2(x))) -> . W1
+                    L_.mlp_bwd(dhpre, dxb, sv[k + "x2"], f["n2g"], f["n2b"], slot(k + "g_mean"), slot(k + "g_rstd"), A["w1t"],
+                               f["fc1_w"], f["fc1_b"], f["fc2_wt"], f["fc1_wt"], dxn, M, C, hid, rp)
+                else:
+                    dy = buf(f"dA{s}", M, C)
+                    L_.gemm(dhpre, A["w1t"], dy, M, C, rp, res1=dxb, groups=2)
+                    dfpre = buf(f"dfpre{s}", M, hid)
+                    L_.gemm(dy, f["fc2_wt"], dfpre, M, hid, C, aux=slot(k + "fpre"), epi=L_.EPI_DGELU)
+                    L_.gemm(dfpre, f["fc1_wt"], dxn, M, C, hid)
                 dx2, dx2b = buf(f"dD{s}", M, C, dtype=sdt), buf(f"dDb{s}", M, C)
                 L_.layernorm_bwd(dxn, sv[k + "x2"], slot(k + "g_mean"), slot(k + "g_rstd"), f["n2g"], dx, dx2, M, C, dx_copy=dx2b)
                 # ---------------- (S) backward: dx2 ----------------

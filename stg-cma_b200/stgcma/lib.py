@@ -25,6 +25,8 @@ _SIGNATURES = {
     "stgcma_layernorm_fwd": [_vp, _fp, _fp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_layernorm_bwd": [_vp, _vp, _fp, _fp, _fp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp],
     "stgcma_gemm": [_vp, _vp, _fp, _vp, _vp, _fp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _i, _i, _vp],
+    "stgcma_mlp_fwd": [_fp, _fp, _fp, _vp, _fp, _vp, _fp, _vp, _fp, _vp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_mlp_bwd": [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_gemm_tn": [_vp, _vp, _fp, _fp, _fp, _fp, _i64, _i, _i, _i64, _i64, _i64, _i, _vp],
     "stgcma_window_attn_fwd": [_vp, _fp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_window_attn_bwd": [_vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
@@ -188,6 +190,25 @@ def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, 
           cost=(2.0 * M * N * K, _es(A) * (M * K + groups * N * K + M * N * (
               0.0 + (res2 is not None) + (aux is not None) + (out_pre is not None))) + _es(out) * M * N * (
               1.0 + (res1 is not None))))
+
+
+def mlp_fused_ok(C, H, rp, dtype, backward=True):
+    """Shapes the fused MLP kernels cover (include/stgcma.h); outside them the engine composes layernorm + gemm."""
+    return (dtype == torch.bfloat16 and C % 32 == 0 and 32 <= C <= (256 if backward else 384) and H % 64 == 0
+            and rp % 16 == 0 and 16 <= rp <= 128)
+
+
+def mlp_fwd(x, gamma, beta, W1, b1, W2, b2, Wa, ba, y, hpre, h, mean, rstd, M, C, H, rp, groups=2):
+    _call("stgcma_mlp_fwd", _p(x), _p(gamma), _p(beta), _p(W1), _p(b1), _p(W2), _p(b2), _p(Wa), _p(ba), _p(y), _p(hpre),
+          _p(h), _p(mean), _p(rstd), M, C, H, rp, groups, dt(y),
+          cost=(2.0 * M * (2 * C * H + C * rp), M * (4.0 * C + 2.0 * C + 4.0 * rp + 8.0)))
+
+
+def mlp_bwd(dhpre, dxb, x, gamma, beta, mean, rstd, Wat, W1, b1, W2t, W1t, dxn, M, C, H, rp, groups=2):
+    # algorithmic FLOPs: the two dX GEMMs of the MLP + the adapter dX GEMM (the fc1 recompute is not counted)
+    _call("stgcma_mlp_bwd", _p(dhpre), _p(dxb), _p(x), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(Wat), _p(W1), _p(b1),
+          _p(W2t), _p(W1t), _p(dxn), M, C, H, rp, groups, dt(dxn),
+          cost=(2.0 * M * (2 * C * H + C * rp), M * (4.0 * C + 2.0 * C + 2.0 * C + 2.0 * rp + 8.0)))
 
 
 def gemm_tn(A, B, dW, M, Ka, Nb, *, lda, ldb, ldo, rowscale=None, csumA=None, csumB=None):

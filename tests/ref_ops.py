@@ -124,6 +124,33 @@ def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, 
         o.copy_(v * _c(_view2d(aux, M, N, ldo)))
 
 
+def mlp_fwd(x, gamma, beta, W1, b1, W2, b2, Wa, ba, y, hpre, h, mean, rstd, M, C, H, rp, groups=2):
+    xx = _c(x).reshape(M, C)
+    mu = xx.mean(1, keepdim=True)
+    var = ((xx - mu) ** 2).mean(1, keepdim=True)
+    rs = torch.rsqrt(var + 1e-5)
+    xn = ((xx - mu) * rs * _c(gamma) + _c(beta)).to(y.dtype)           # the kernel's A operand is in the activation dtype
+    hid = _gelu(_c(xn) @ _c(W1).t() + _c(b1)).to(y.dtype)
+    yy = (_c(hid) @ _c(W2).t() + _c(b2)).to(y.dtype)
+    y.reshape(M, C).copy_(yy)
+    Mg = M // groups
+    pre = torch.einsum("gmk,gnk->gmn", _c(yy).reshape(groups, Mg, C), _c(Wa).reshape(groups, rp, C)) + _c(ba).reshape(groups, 1, rp)
+    hpre.reshape(M, rp).copy_(pre.reshape(M, rp))
+    h.reshape(M, rp).copy_(_gelu(pre).reshape(M, rp))
+    mean.copy_(mu.reshape(M))
+    rstd.copy_(rs.reshape(M))
+
+
+def mlp_bwd(dhpre, dxb, x, gamma, beta, mean, rstd, Wat, W1, b1, W2t, W1t, dxn, M, C, H, rp, groups=2):
+    xn = ((_c(x).reshape(M, C) - _c(mean).reshape(M, 1)) * _c(rstd).reshape(M, 1) * _c(gamma) + _c(beta)).to(dxn.dtype)
+    Mg = M // groups
+    dy = torch.einsum("gmk,gnk->gmn", _c(dhpre).reshape(groups, Mg, rp), _c(Wat).reshape(groups, C, rp)).reshape(M, C)
+    dy = (dy + _c(dxb).reshape(M, C)).to(dxn.dtype)
+    fpre = _c(xn) @ _c(W1).t() + _c(b1)
+    df = ((_c(dy) @ _c(W2t).t()) * _dgelu(fpre)).to(dxn.dtype)
+    dxn.reshape(M, C).copy_(_c(df) @ _c(W1t).t())
+
+
 def gemm_tn(A, B, dW, M, Ka, Nb, *, lda, ldb, ldo, rowscale=None, csumA=None, csumB=None):
     a = _c(_view2d(A, M, Ka, lda))
     b = _c(_view2d(B, M, Nb, ldb))
@@ -313,7 +340,7 @@ def install_fake_backend(monkeypatch, lib_module):
     """Route every kernel wrapper of stgcma.lib to the torch references above (CPU tests only)."""
     import sys
     me = sys.modules[__name__]
-    for name in ("patch_embed_fwd", "layernorm_fwd", "layernorm_bwd", "gemm", "gemm_tn", "window_attn_fwd",
+    for name in ("patch_embed_fwd", "layernorm_fwd", "layernorm_bwd", "gemm", "gemm_tn", "mlp_fwd", "mlp_bwd", "window_attn_fwd",
                  "window_attn_bwd", "temporal_attn_fwd", "temporal_attn_bwd", "xmodal_window_fwd", "xmodal_window_bwd",
                  "xmodal_global_fwd", "xmodal_global_bwd", "head_pool_fwd", "head_pool_bwd", "pack_params"):
         monkeypatch.setattr(lib_module, name, getattr(me, name))

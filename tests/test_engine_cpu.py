@@ -40,10 +40,14 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
+@pytest.mark.parametrize("fused_mlp", [False, True])
 @pytest.mark.parametrize("mode", ["fusion", "multimodal"])
-def test_schedule_matches_oracle(monkeypatch, mode):
+def test_schedule_matches_oracle(monkeypatch, mode, fused_mlp):
+    """fused_mlp: the bf16 production schedule (stgcma_mlp_fwd / _bwd instead of layernorm + 3 gemm calls per
+    direction), exercised here in fp64 through the torch references of those two entry points."""
     import stgcma.lib
     ref_ops.install_fake_backend(monkeypatch, stgcma.lib)
+    monkeypatch.setattr(stgcma.lib, "mlp_fused_ok", lambda *a, **k: fused_mlp)
     cfg = O.SwinAVEConfig(**TINY)
     sd = O.make_state(cfg, seed=3, dtype=torch.float64)
     a, v, labels = O.make_inputs(cfg, 2, seed=3, dtype=torch.float64)

@@ -79,6 +79,77 @@ def test_gemm(case, dtype):
     if out_pre is not None:
         assert rel(out_pre, r_pre) < TOL[dtype]
 
+# ---------------------------------------------------------------------------------------------
+# fused frozen MLP (bf16 only): LN2 -> fc1 -> GELU -> fc2 -> adapter fc1 (+GELU), and its dX backward
+MLP_CASES = [
+    # M, C, H, rp   (groups = 2)
+    (2 * 300, 96, 384, 16),       # Swin-T stage 0: K tail (96 = 64 + 32), ragged last tile per group, 2 CTAs / SM
+    (2 * 128, 32, 128, 16),       # the tiny test model
+    (2 * 1000, 128, 512, 16),     # Swin-B stage 0
+    (2 * 200, 192, 768, 32),      # Swin-T stage 1: 128-wide hidden chunks
+    (2 * 260, 192, 768, 96),      # Swin-L stage 0 adapter width: two k-blocks of rp in the backward
+    (2 * 130, 256, 1024, 32),     # Swin-B stage 1
+    (2 * 20000, 96, 384, 16),     # many tiles per CTA: barrier phases over a long persistent loop
+]
+
+
+def _mlp_inputs(M, C, H, rp):
+    dt = torch.bfloat16
+    x = rnd(M, C, dtype=torch.float32, seed=1, scale=2.0) + 0.5
+    gamma = (1.0 + 0.2 * rnd(C, dtype=torch.float32, seed=2))
+    beta = 0.1 * rnd(C, dtype=torch.float32, seed=3)
+    W1 = rnd(H, C, dtype=dt, seed=4, scale=C ** -0.5)
+    b1 = 0.2 * rnd(H, dtype=torch.float32, seed=5)
+    W2 = rnd(C, H, dtype=dt, seed=6, scale=H ** -0.5)
+    b2 = 0.2 * rnd(C, dtype=torch.float32, seed=7)
+    Wa = rnd(2, rp, C, dtype=dt, seed=8, scale=C ** -0.5)
+    ba = 0.2 * rnd(2, rp, dtype=torch.float32, seed=9)
+    return x, gamma, beta, W1, b1, W2, b2, Wa, ba
+
+
+@pytest.mark.parametrize("case", MLP_CASES, ids=lambda c: f"M{c[0]}C{c[1]}H{c[2]}r{c[3]}")
+def test_mlp_fwd(case):
+    M, C, H, rp = case
+    dt = torch.bfloat16
+    x, gamma, beta, W1, b1, W2, b2, Wa, ba = _mlp_inputs(M, C, H, rp)
+    nan = float("nan")
+    y = torch.full((M, C), nan, dtype=dt, device="cuda")
+    hpre, h = torch.full((M, rp), nan, dtype=dt, device="cuda"), torch.full((M, rp), nan, dtype=dt, device="cuda")
+    mean, rstd = torch.full((M,), nan, device="cuda"), torch.full((M,), nan, device="cuda")
+    L().mlp_fwd(x, gamma, beta, W1, b1, W2, b2, Wa, ba, y, hpre, h, mean, rstd, M, C, H, rp)
+    torch.cuda.synchronize()
+    f64 = torch.float64
+    r_y, r_hpre, r_h = torch.empty(M, C, dtype=dt), torch.empty(M, rp, dtype=f64), torch.empty(M, rp, dtype=f64)
+    r_mean, r_rstd = torch.empty(M, dtype=f64), torch.empty(M, dtype=f64)
+    R.mlp_fwd(cpu(x), cpu(gamma), cpu(beta), cpu(W1), cpu(b1), cpu(W2), cpu(b2), cpu(Wa), cpu(ba), r_y, r_hpre, r_h, r_mean,
+              r_rstd, M, C, H, rp)
+    for t in (y, hpre, h, mean, rstd):
+        assert torch.isfinite(t.float()).all()
+    assert rel(mean, r_mean) < 1e-5 and rel(rstd, r_rstd) < 1e-5
+    assert rel(y, r_y) < 1e-2
+    assert rel(hpre, r_hpre) < 1e-2 and rel(h, r_h) < 1e-2
+
+
+@pytest.mark.parametrize("case", [c for c in MLP_CASES if c[1] <= 256], ids=lambda c: f"M{c[0]}C{c[1]}H{c[2]}r{c[3]}")
+def test_mlp_bwd(case):
+    M, C, H, rp = case
+    dt = torch.bfloat16
+    x, gamma, beta, W1, b1, W2, b2, Wa, ba = _mlp_inputs(M, C, H, rp)
+    mu = x.mean(1)
+    rs = torch.rsqrt(x.var(1, unbiased=False) + 1e-5)
+    dhpre = rnd(M, rp, dtype=dt, seed=11)
+    dxb = rnd(M, C, dtype=dt, seed=12)
+    Wat = Wa.transpose(1, 2).contiguous()
+    W2t, W1t = W2.t().contiguous(), W1.t().contiguous()
+    dxn = torch.full((M, C), float("nan"), dtype=dt, device="cuda")
+    L().mlp_bwd(dhpre, dxb, x, gamma, beta, mu, rs, Wat, W1, b1, W2t, W1t, dxn, M, C, H, rp)
+    torch.cuda.synchronize()
+    r = torch.empty(M, C, dtype=dt)       # the reference rounds its intermediates like the kernel (bf16 operands)
+    R.mlp_bwd(cpu(dhpre), cpu(dxb), cpu(x), cpu(gamma), cpu(beta), cpu(mu), cpu(rs), cpu(Wat), cpu(W1), cpu(b1), cpu(W2t),
+              cpu(W1t), r, M, C, H, rp)
+    assert torch.isfinite(dxn.float()).all()
+    assert rel(dxn, r) < 1e-2
+
 
 def test_gemm_bf16_padded_strides():
     """lda / ldo larger than the logical width (adapter hidden tensors are stored padded)."""
