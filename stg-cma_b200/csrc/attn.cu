@@ -287,6 +287,11 @@ __global__ void __launch_bounds__(128) temporal_attn_bwd_kernel(const T* __restr
   if (threadIdx.x < 2 * Tn - 1) atomicAdd(dtbl + ((int64_t)g * (2 * Tn - 1) + threadIdx.x) * heads + h, dbias[threadIdx.x]);
 }
 
+// bf16 production kernels (tensor cores), temporal_tc.cu; -1 = shape not covered
+int temporal_attn_fwd_bf16(const void* qkv, const float* tbl, void* out, int G, int B, int T, int L, int heads,
+                           cudaStream_t st);
+int temporal_attn_bwd_bf16(const void* qkv, const float* tbl, const void* dout, void* dqkv, float* dtbl, int G, int B, int T,
+                           int L, int heads, cudaStream_t st);
 // bf16 production kernels (tensor cores), attn_tc.cu
 int window_attn_fwd_bf16(const void* qkv, const float* rpb, void* out, int64_t frames, int R, int ws, int shift, int heads,
                          cudaStream_t st);
@@ -346,8 +351,11 @@ extern "C" int stgcma_temporal_attn_fwd(const void* qkv, const float* tbl, void*
   dim3 grid((unsigned)ceil_div((int64_t)B * L, 4), G * heads);
   if (dtype == STGCMA_F32)
     temporal_attn_fwd_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, tbl, (float*)out, B, T, L, heads);
-  else if (dtype == STGCMA_BF16)
+  else if (dtype == STGCMA_BF16) {
+    const int rc = temporal_attn_fwd_bf16(qkv, tbl, out, G, B, T, L, heads, st);   // tensor-core kernel
+    if (rc != -1) return rc;
     temporal_attn_fwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)qkv, tbl, (bf16*)out, B, T, L, heads);
+  }
   else
     STG_REQUIRE(false, "temporal_attn_fwd: bad dtype %d", dtype);
   return check_launch("temporal_attn_fwd");
@@ -363,8 +371,11 @@ extern "C" int stgcma_temporal_attn_bwd(const void* qkv, const float* tbl, const
   dim3 grid((unsigned)ceil_div((int64_t)B * L, 4), G * heads);
   if (dtype == STGCMA_F32)
     temporal_attn_bwd_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, tbl, (const float*)dout, (float*)dqkv, dtbl, B, T, L, heads);
-  else if (dtype == STGCMA_BF16)
+  else if (dtype == STGCMA_BF16) {
+    const int rc = temporal_attn_bwd_bf16(qkv, tbl, dout, dqkv, dtbl, G, B, T, L, heads, st);
+    if (rc != -1) return rc;
     temporal_attn_bwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)qkv, tbl, (const bf16*)dout, (bf16*)dqkv, dtbl, B, T, L, heads);
+  }
   else
     STG_REQUIRE(false, "temporal_attn_bwd: bad dtype %d", dtype);
   return check_launch("temporal_attn_bwd");

@@ -1,0 +1,355 @@
+// Temporal attention (WindowAttention.forward, temporal=True; Swin_AVE.py:244-255), bf16 production kernels.
+//
+//   sequence = the T frames of one (modality g, clip b, token n); per head (dim 32):
+//       S[i][j] = (q_i . k_j) / sqrt(32) + tbl_g[i - j + T - 1][head]      P = softmax_j S      o_i = sum_j P[i][j] v_j
+//
+// The '(b t) n c -> (b n) t c' rearranges (:706-716) are folded into the addressing: a CTA owns NT consecutive
+// tokens of one (g, b) and loads, for each frame t, the NT * 3C contiguous channels of those tokens with 16-byte
+// cp.async -- every global access of the kernel is a full-line burst (the previous kernel read 64-byte pieces).
+// One warp processes one (token, head) pair at a time on the warp-level tensor cores (mma.sync m16n8k16; T <= 16 is
+// one 16 x 16 score tile): Q K^T, softmax in registers, P V.  Results overwrite the task's own q (fwd) / q, k, v
+// (bwd) slots of the shared tile, which is then written back with coalesced 16-byte stores.
+//   backward: dS = P o (dP - rowsum(P o dP)),  dQ = dS K / sqrt(32),  dK = dS^T Q / sqrt(32),  dV = P^T dO, and the
+//   gradient of the TRAINABLE bias table, dtbl[i - j + T - 1][head] += dS[i][j].  The transposed products use a
+//   second, transposed score tile (K Q^T) instead of transposing fragments.  dtbl is accumulated in shared memory
+//   over the CTA's whole (persistent) tile loop and flushed once: a few thousand global atomics per launch.
+#include "mma.cuh"
+
+namespace stgcma {
+namespace ttc {
+
+using namespace mma;
+
+constexpr int HD = 32;
+constexpr float kScale = 0.17677669529663689f;   // 32^-0.5
+
+struct Geo {
+  int T, L, heads, C, NT;
+  int row3;      // bytes of one token row of qkv   (3C * 2)
+  int row1;      // bytes of one token row of out   (C * 2)
+  int ts3, ts1;  // byte stride between frames in the shared tiles (NT * row + pad, == 16 mod 128)
+};
+
+__device__ __forceinline__ int clampi(int r, int T) { return r < T ? r : T - 1; }
+
+// fragments from a [t][.] tile whose frame stride is `ts` bytes; rows (frames) >= T are clamped to T - 1
+__device__ __forceinline__ void lda(uint32_t (&a)[4], const uint8_t* base, int ts, int k0, int T, int lane) {
+  const int r = clampi((lane & 7) + ((lane >> 3) & 1) * 8, T);
+  ldsm_x4(a, smem_addr(base + r * ts + (k0 + (lane >> 4) * 8) * 2));
+}
+__device__ __forceinline__ void ldb_nk(uint32_t (&b)[4], const uint8_t* base, int ts, int k0, int T, int lane) {
+  const int n = clampi((lane & 7) + (lane >> 4) * 8, T);
+  ldsm_x4(b, smem_addr(base + n * ts + (k0 + ((lane >> 3) & 1) * 8) * 2));
+}
+__device__ __forceinline__ void ldb_kn(uint32_t (&b)[4], const uint8_t* base, int ts, int n0, int T, int lane) {
+  const int k = clampi((lane & 7) + ((lane >> 3) & 1) * 8, T);
+  ldsm_x4_t(b, smem_addr(base + k * ts + (n0 + (lane >> 4) * 8) * 2));
+}
+
+// D[16 x 16] = A[16 x 32] . B[16 x 32]^T   (A rows from `a`, B rows from `b`, both [t][32] slices)
+__device__ __forceinline__ void mm_nt(float (&d)[2][4], const uint8_t* a, int tsa, const uint8_t* b, int tsb, int T, int lane) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t fa[4], fb[4];
+    lda(fa, a, tsa, ks * 16, T, lane);
+    ldb_nk(fb, b, tsb, ks * 16, T, lane);
+    mma16816(d[0], fa, fb[0], fb[1]);
+    mma16816(d[1], fa, fb[2], fb[3]);
+  }
+}
+// D[16 x 32] = P[16 x 16] . B[16 x 32]   (P in accumulator layout, B rows = contraction index)
+__device__ __forceinline__ void mm_pv(float (&d)[4][4], const float (&p)[2][4], const uint8_t* b, int tsb, int T, int lane) {
+  uint32_t pa[4];
+  pa[0] = pack_bf16(p[0][0], p[0][1]);
+  pa[1] = pack_bf16(p[0][2], p[0][3]);
+  pa[2] = pack_bf16(p[1][0], p[1][1]);
+  pa[3] = pack_bf16(p[1][2], p[1][3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+#pragma unroll
+  for (int n2 = 0; n2 < 2; ++n2) {
+    uint32_t fb[4];
+    ldb_kn(fb, b, tsb, n2 * 16, T, lane);
+    mma16816(d[2 * n2], pa, fb[0], fb[1]);
+    mma16816(d[2 * n2 + 1], pa, fb[2], fb[3]);
+  }
+}
+
+// writes a [16 x 32] accumulator (rows = frames) into a [t][32] slice, rows < T only
+__device__ __forceinline__ void store_rows(uint8_t* dst, int ts, const float (&d)[4][4], float scale, int T, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int col = i * 8 + 2 * t;
+    if (g < T) *reinterpret_cast<uint32_t*>(dst + g * ts + col * 2) = pack_bf16(d[i][0] * scale, d[i][1] * scale);
+    if (g + 8 < T) *reinterpret_cast<uint32_t*>(dst + (g + 8) * ts + col * 2) = pack_bf16(d[i][2] * scale, d[i][3] * scale);
+  }
+}
+
+// copies NT token rows x T frames between global ([T frames L rows apart][row bytes]) and the shared tile
+template <bool TO_SMEM>
+__device__ __forceinline__ void copy_tile(uint8_t* tile, int ts, uint8_t* gbase, int64_t frame_stride_bytes, int rowbytes,
+                                          int nt, int T, int tid, int nthr) {
+  const int cpr = nt * rowbytes / 16;   // 16-byte chunks per frame (the nt rows are contiguous)
+  for (int e = tid; e < T * cpr; e += nthr) {
+    const int t = e / cpr, c = e - t * cpr;
+    uint8_t* s = tile + t * ts + c * 16;
+    uint8_t* gp = gbase + t * frame_stride_bytes + (int64_t)c * 16;
+    if (TO_SMEM) cp_async16(s, gp);
+    else *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(s);
+  }
+}
+
+// softmax of a 16 x 16 score tile held in accumulator layout; returns P in place and the row lse (log2 domain)
+__device__ __forceinline__ void bias_softmax(float (&s)[2][4], const float* tbs, int heads, int T, int lane, float& lse0,
+                                             float& lse1) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
+      s[nt][e] = (j < T && i < T) ? (s[nt][e] * kScale + tbs[(i - j + T - 1) * heads]) * kLog2e : -INFINITY;
+    }
+  float m0 = quad_max(fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1])));
+  float m1 = quad_max(fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3])));
+  if (m0 == -INFINITY) m0 = 0.f;   // padding rows (i >= T): all -inf
+  if (m1 == -INFINITY) m1 = 0.f;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    s[nt][0] = ex2(s[nt][0] - m0);
+    s[nt][1] = ex2(s[nt][1] - m0);
+    s[nt][2] = ex2(s[nt][2] - m1);
+    s[nt][3] = ex2(s[nt][3] - m1);
+    l0 += s[nt][0] + s[nt][1];
+    l1 += s[nt][2] + s[nt][3];
+  }
+  l0 = quad_sum(l0);
+  l1 = quad_sum(l1);
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    s[nt][0] *= i0;
+    s[nt][1] *= i0;
+    s[nt][2] *= i1;
+    s[nt][3] *= i1;
+  }
+  lse0 = l0 > 0.f ? m0 + log2f(l0) : INFINITY;
+  lse1 = l1 > 0.f ? m1 + log2f(l1) : INFINITY;
+}
+
+__device__ __forceinline__ void tile_coords(int64_t tile, int tiles_per_seq, int B, int NT, int& g, int& b, int& n0) {
+  const int tl = (int)(tile % tiles_per_seq);
+  const int64_t gb = tile / tiles_per_seq;
+  b = (int)(gb % B);
+  g = (int)(gb / B);
+  n0 = tl * NT;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tt_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ tbl,
+                                                     bf16* __restrict__ out, int G, int B, Geo geo) {
+  extern __shared__ __align__(16) uint8_t tsm[];
+  uint8_t* tile = tsm;                                               // [T][NT][3C] (+pad per frame)
+  float* tb_s = reinterpret_cast<float*>(tile + geo.T * geo.ts3);    // [G][2T-1][heads]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = geo.T, L = geo.L, NT = geo.NT, heads = geo.heads;
+  const int nb = 2 * T - 1;
+  for (int i = tid; i < G * nb * heads; i += 256) tb_s[i] = tbl[i];
+  const int tiles_per_seq = (L + NT - 1) / NT;
+  const int64_t ntiles = (int64_t)G * B * tiles_per_seq;
+  for (int64_t tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+    int g, b, n0;
+    tile_coords(tile_i, tiles_per_seq, B, NT, g, b, n0);
+    const int nt = (L - n0) < NT ? (L - n0) : NT;
+    const int64_t row0 = ((int64_t)g * B + b) * T * L + n0;   // token row of frame 0
+    __syncthreads();   // the previous tile has been written back; tb_s is loaded
+    copy_tile<true>(tile, geo.ts3, (uint8_t*)(qkv + row0 * 3 * geo.C), (int64_t)L * geo.row3, geo.row3, nt, T, tid, 256);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int task = warp; task < nt * heads; task += 8) {
+      const int n = task / heads, h = task - n * heads;
+      uint8_t* qb = tile + n * geo.row3 + h * (HD * 2);
+      const uint8_t* kb = qb + geo.C * 2;
+      const uint8_t* vb = qb + geo.C * 4;
+      const float* tbs = tb_s + (g * nb) * heads + h;
+      float s[2][4], lse0, lse1;
+      mm_nt(s, qb, geo.ts3, kb, geo.ts3, T, lane);
+      bias_softmax(s, tbs, heads, T, lane, lse0, lse1);
+      float o[4][4];
+      mm_pv(o, s, vb, geo.ts3, T, lane);
+      __syncwarp();
+      store_rows(qb, geo.ts3, o, 1.0f, T, lane);   // o overwrites this task's q slot
+    }
+    __syncthreads();
+    // write back the q slots ([t][n][0..C)) as out[t][n][C]
+    {
+      const int cpr = geo.row1 / 16;
+      for (int e = tid; e < T * nt * cpr; e += 256) {
+        const int t = e / (nt * cpr), rem = e - t * nt * cpr, n = rem / cpr, c = rem - n * cpr;
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out + (row0 + (int64_t)t * L + n) * geo.C) + c * 16) =
+            *reinterpret_cast<const uint4*>(tile + t * geo.ts3 + n * geo.row3 + c * 16);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tt_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ tbl,
+                                                     const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+                                                     float* __restrict__ dtbl, int G, int B, Geo geo) {
+  extern __shared__ __align__(16) uint8_t tsm[];
+  uint8_t* tile = tsm;                                               // [T][NT][3C]
+  uint8_t* dtile = tile + geo.T * geo.ts3;                           // [T][NT][C]  dout
+  float* tb_s = reinterpret_cast<float*>(dtile + geo.T * geo.ts1);   // [G][2T-1][heads]
+  float* db_s = tb_s + G * (2 * geo.T - 1) * geo.heads;              // [G][2T-1][heads] gradient accumulator
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int T = geo.T, L = geo.L, NT = geo.NT, heads = geo.heads;
+  const int nb = 2 * T - 1;
+  for (int i = tid; i < G * nb * heads; i += 256) {
+    tb_s[i] = tbl[i];
+    db_s[i] = 0.f;
+  }
+  const int tiles_per_seq = (L + NT - 1) / NT;
+  const int64_t ntiles = (int64_t)G * B * tiles_per_seq;
+  for (int64_t tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+    int g, b, n0;
+    tile_coords(tile_i, tiles_per_seq, B, NT, g, b, n0);
+    const int nt = (L - n0) < NT ? (L - n0) : NT;
+    const int64_t row0 = ((int64_t)g * B + b) * T * L + n0;
+    __syncthreads();
+    copy_tile<true>(tile, geo.ts3, (uint8_t*)(qkv + row0 * 3 * geo.C), (int64_t)L * geo.row3, geo.row3, nt, T, tid, 256);
+    copy_tile<true>(dtile, geo.ts1, (uint8_t*)(dout + row0 * geo.C), (int64_t)L * geo.row1, geo.row1, nt, T, tid, 256);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int task = warp; task < nt * heads; task += 8) {
+      const int n = task / heads, h = task - n * heads;
+      uint8_t* qb = tile + n * geo.row3 + h * (HD * 2);
+      uint8_t* kb = qb + geo.C * 2;
+      uint8_t* vb = qb + geo.C * 4;
+      const uint8_t* ob = dtile + n * geo.row1 + h * (HD * 2);
+      const float* tbs = tb_s + (g * nb) * heads + h;
+      float* dbs = db_s + (g * nb) * heads + h;
+      // ---- direct tile: rows i (queries), columns j (keys) ----
+      float p[2][4], dp[2][4], lse0, lse1;
+      mm_nt(p, qb, geo.ts3, kb, geo.ts3, T, lane);
+      bias_softmax(p, tbs, heads, T, lane, lse0, lse1);
+      mm_nt(dp, ob, geo.ts1, vb, geo.ts3, T, lane);          // dP = dO V^T
+      float dl0 = quad_sum(p[0][0] * dp[0][0] + p[0][1] * dp[0][1] + p[1][0] * dp[1][0] + p[1][1] * dp[1][1]);
+      float dl1 = quad_sum(p[0][2] * dp[0][2] + p[0][3] * dp[0][3] + p[1][2] * dp[1][2] + p[1][3] * dp[1][3]);
+      float ds[2][4];
+#pragma unroll
+      for (int nt2 = 0; nt2 < 2; ++nt2)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = gq + (e >> 1) * 8, j = nt2 * 8 + 2 * tq + (e & 1);
+          const float v = p[nt2][e] * (dp[nt2][e] - ((e & 2) ? dl1 : dl0));   // p == 0 on padding
+          ds[nt2][e] = v;
+          if (i < T && j < T) atomicAdd(dbs + (i - j + T - 1) * heads, v);   // the bias enters the logits un-scaled
+        }
+      float dq[4][4];
+      mm_pv(dq, ds, kb, geo.ts3, T, lane);                   // dQ = dS K
+      // ---- transposed tile: rows j (keys), columns i (queries) ----
+      float pt[2][4], dpt[2][4];
+      mm_nt(pt, kb, geo.ts3, qb, geo.ts3, T, lane);          // S^T = K Q^T
+      mm_nt(dpt, vb, geo.ts3, ob, geo.ts1, T, lane);         // dP^T = V dO^T
+      // lse / dl of query i live in the quad of lanes 4 (i % 8) .. + 3 (lse0 / dl0: i < 8, lse1 / dl1: i >= 8)
+      float dst_[2][4];
+#pragma unroll
+      for (int nt2 = 0; nt2 < 2; ++nt2)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = gq + (e >> 1) * 8, i = nt2 * 8 + 2 * tq + (e & 1);
+          const int src = 4 * (2 * tq + (e & 1));
+          const float lse_i = __shfl_sync(0xffffffffu, nt2 ? lse1 : lse0, src);
+          const float dl_i = __shfl_sync(0xffffffffu, nt2 ? dl1 : dl0, src);
+          float pv = 0.f;
+          if (i < T && j < T) pv = ex2((pt[nt2][e] * kScale + tbs[(i - j + T - 1) * heads]) * kLog2e - lse_i);
+          pt[nt2][e] = pv;
+          dst_[nt2][e] = pv * (dpt[nt2][e] - dl_i);
+        }
+      float dk[4][4], dv[4][4];
+      mm_pv(dk, dst_, qb, geo.ts3, T, lane);                 // dK = dS^T Q
+      mm_pv(dv, pt, ob, geo.ts1, T, lane);                   // dV = P^T dO
+      __syncwarp();
+      store_rows(qb, geo.ts3, dq, kScale, T, lane);
+      store_rows(kb, geo.ts3, dk, kScale, T, lane);
+      store_rows(vb, geo.ts3, dv, 1.0f, T, lane);
+    }
+    __syncthreads();
+    copy_tile<false>(tile, geo.ts3, (uint8_t*)(dqkv + row0 * 3 * geo.C), (int64_t)L * geo.row3, geo.row3, nt, T, tid, 256);
+  }
+  __syncthreads();
+  for (int i = tid; i < G * nb * heads; i += 256) {
+    const float v = db_s[i];
+    if (v != 0.f) atomicAdd(dtbl + i, v);
+  }
+}
+
+static bool make_geo(Geo& geo, int T, int L, int heads) {
+  geo.T = T;
+  geo.L = L;
+  geo.heads = heads;
+  geo.C = heads * HD;
+  geo.row3 = 3 * geo.C * 2;
+  geo.row1 = geo.C * 2;
+  // tokens per tile: keep the qkv tile around 48 KB so that several CTAs share an SM
+  int nt = (48 * 1024) / (T * geo.row3);
+  if (nt < 1) nt = 1;
+  if (nt > 8) nt = 8;
+  if (nt > L) nt = L;
+  geo.NT = nt;
+  auto pad16 = [](int bytes) { return bytes + ((16 - (bytes % 128)) + 128) % 128; };   // stride == 16 (mod 128)
+  geo.ts3 = pad16(nt * geo.row3);
+  geo.ts1 = pad16(nt * geo.row1);
+  return true;
+}
+
+}  // namespace ttc
+
+int temporal_attn_fwd_bf16(const void* qkv, const float* tbl, void* out, int G, int B, int T, int L, int heads,
+                           cudaStream_t st) {
+  using namespace ttc;
+  if (T > 16 || T < 1) return -1;
+  Geo geo;
+  make_geo(geo, T, L, heads);
+  const size_t smem = (size_t)T * geo.ts3 + (size_t)G * (2 * T - 1) * heads * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  cudaError_t e = cudaFuncSetAttribute(tt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("temporal_attn_fwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
+  const int64_t ntiles = (int64_t)G * B * ceil_div(L, geo.NT);
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
+  tt_fwd_kernel<<<grid, 256, smem, st>>>((const bf16*)qkv, tbl, (bf16*)out, G, B, geo);
+  return check_launch("temporal_attn_fwd(tc)");
+}
+
+int temporal_attn_bwd_bf16(const void* qkv, const float* tbl, const void* dout, void* dqkv, float* dtbl, int G, int B, int T,
+                           int L, int heads, cudaStream_t st) {
+  using namespace ttc;
+  if (T > 16 || T < 1) return -1;
+  Geo geo;
+  make_geo(geo, T, L, heads);
+  const size_t smem = (size_t)T * (geo.ts3 + geo.ts1) + (size_t)2 * G * (2 * T - 1) * heads * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  cudaError_t e = cudaFuncSetAttribute(tt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("temporal_attn_bwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
+  const int64_t ntiles = (int64_t)G * B * ceil_div(L, geo.NT);
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
+  tt_bwd_kernel<<<grid, 256, smem, st>>>((const bf16*)qkv, tbl, (const bf16*)dout, (bf16*)dqkv, dtbl, G, B, geo);
+  return check_launch("temporal_attn_bwd(tc)");
+}
+
+}  // namespace stgcma

@@ -470,6 +470,11 @@ int xmodal_global_fwd_bf16(const void* h, const float* gate, void* out, void* at
                            int rp, cudaStream_t st);
 int xmodal_global_bwd_bf16(const void* h, const void* hpre, const float* gate, const float* lse, const float* D,
                            const void* dout, void* dh, int64_t frames, int L, int rp, cudaStream_t st);
+// xmodal_win_tc.cu
+int xmodal_window_fwd_bf16(const void* h, const float* gate, void* out, void* attn_out, int64_t frames, int R, int ws,
+                           int shift, int rp, cudaStream_t st);
+int xmodal_window_bwd_bf16(const void* h, const void* hpre, const float* gate, const void* attn_out, const void* dout,
+                           void* dh, float* dgate, int64_t frames, int R, int ws, int shift, int rp, cudaStream_t st);
 
 }  // namespace stgcma
 
@@ -498,6 +503,8 @@ extern "C" int stgcma_xmodal_window_fwd(const void* h, const float* gate, void* 
     if (e != cudaSuccess) { set_error("xmodal_window_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
     xmodal_window_fwd_kernel<float><<<grid, 128, smem, st>>>((const float*)h, gate, (float*)out, (float*)attn_out, frames, R, ws, shift, rp);
   } else if (dtype == STGCMA_BF16) {
+    rc = xmodal_window_fwd_bf16(h, gate, out, attn_out, frames, R, ws, shift, rp, st);   // tensor-core kernel
+    if (rc != -1) return rc;
     e = cudaFuncSetAttribute(xmodal_window_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("xmodal_window_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
     xmodal_window_fwd_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)h, gate, (bf16*)out, (bf16*)attn_out, frames, R, ws, shift, rp);
@@ -524,6 +531,8 @@ extern "C" int stgcma_xmodal_window_bwd(const void* h, const void* hpre, const f
     xmodal_window_bwd_kernel<float><<<grid, 128, smem, st>>>((const float*)h, (const float*)hpre, gate, (const float*)attn_out,
                                                              (const float*)dout, (float*)dh, dgate, frames, R, ws, shift, rp);
   } else if (dtype == STGCMA_BF16) {
+    rc = xmodal_window_bwd_bf16(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, shift, rp, st);
+    if (rc != -1) return rc;
     e = cudaFuncSetAttribute(xmodal_window_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("xmodal_window_bwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
     xmodal_window_bwd_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)h, (const bf16*)hpre, gate, (const bf16*)attn_out,

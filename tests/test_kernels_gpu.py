@@ -315,7 +315,8 @@ def test_window_attention(Rr, ws, shift, heads, frames, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("G,B,T,Ln,heads", [(2, 2, 10, 49, 2), (2, 1, 3, 30, 1), (1, 3, 16, 5, 3)])
+@pytest.mark.parametrize("G,B,T,Ln,heads", [(2, 2, 10, 49, 2), (2, 1, 3, 30, 1), (1, 3, 16, 5, 3), (2, 2, 10, 3136, 3),
+                                             (2, 1, 10, 196, 12), (2, 1, 10, 50, 24), (1, 1, 2, 7, 1), (2, 3, 10, 797, 6)])
 def test_temporal_attention(G, B, T, Ln, heads, dtype):
     C = heads * 32
     rows = G * B * T * Ln
@@ -344,7 +345,9 @@ def _h_inputs(rows2, rp, r, dtype, seed):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("frames,Rr,ws,shift,rp,r", [(3, 14, 7, 0, 16, 12), (2, 14, 7, 3, 32, 24), (4, 7, 7, 0, 48, 48)])
+@pytest.mark.parametrize("frames,Rr,ws,shift,rp,r", [(3, 14, 7, 0, 16, 12), (2, 14, 7, 3, 32, 24), (4, 7, 7, 0, 48, 48),
+                                                    (1, 56, 7, 3, 16, 12), (2, 8, 4, 1, 16, 16), (1, 28, 7, 3, 96, 96),
+                                                    (1, 14, 7, 0, 64, 64)])
 def test_xmodal_window(frames, Rr, ws, shift, rp, r, dtype):
     rows = frames * Rr * Rr
     h = _h_inputs(2 * rows, rp, r, dtype, 1)
