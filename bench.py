@@ -186,11 +186,13 @@ def ours(args):
     ms_e2e = timed(step_e2e, args.steps)
 
     # one profiled step: per-kernel CUDA-event durations (not part of any reported throughput)
+    # every rank runs the step (its backward holds the gradient all-reduce); only rank 0 brackets the launches
     prof = None
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
         lib.profile_start()
-        step_resident()
+    step_resident()
+    if rank == 0:
         prof = lib.profile_stop()
     barrier()
 
@@ -205,15 +207,18 @@ def ours(args):
     tot_ms = sum(d["ms"] for d in prof.values()) or 1.0
     shares = {k.replace("stgcma_", ""): round(d["ms"] / tot_ms, 4) for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     top_name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    if top["flops"] > 0 and top_name in ("stgcma_gemm", "stgcma_gemm_tn", "stgcma_xmodal_global_fwd", "stgcma_xmodal_global_bwd",
-                                         "stgcma_window_attn_fwd", "stgcma_window_attn_bwd"):
-        ach = top["flops"] / (top["ms"] / 1e3) / 1e12
-        roof = {"kernel": top_name, "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": None}
+    # The dominant kernel class is judged against the roof it is closest to: a GEMM with K = 96 (Swin stage 0) has
+    # ~70 FLOP per byte, far below the B200 ridge (~250), so its roof is HBM, not the tensor pipe.  Both fractions
+    # are reported; `bound` names the larger one.
+    tf = top["flops"] / (top["ms"] / 1e3) / 1e12
+    gbs = top["bytes"] / (top["ms"] / 1e3) / 1e9
+    f_tensor, f_hbm = tf / pk["tf_sustained"], gbs / pk["hbm"]
+    if top["flops"] > 0 and f_tensor >= f_hbm:
+        roof = {"kernel": top_name, "bound": "tensor", "achieved": round(tf, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(f_tensor, 4), "traffic": None, "hbm_frac": round(f_hbm, 4)}
     else:
-        ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
-        roof = {"kernel": top_name, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
-                "frac": round(ach / pk["hbm"], 4), "traffic": None}
+        roof = {"kernel": top_name, "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
+                "frac": round(f_hbm, 4), "traffic": None, "tensor_frac": round(f_tensor, 4)}
     roof["peak_source"] = pk["source"] + ("; sustained figure: kernel timed inside a long step" if roof["bound"] == "tensor" else "")
     roof["launches"] = top["calls"]
     roof["avg_launch_ms"] = round(top["ms"] / top["calls"], 4)
@@ -289,7 +294,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="swin_t", choices=list(FLOPS_PER_CLIP))
-    ap.add_argument("--batch", type=int, default=16, help="clips per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

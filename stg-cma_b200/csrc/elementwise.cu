@@ -158,7 +158,7 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
 // with coalesced loads, the [Cin*16, C] transposed weight stays resident in smem, each warp
 // produces whole tokens (lane = channel mod 32) so the LayerNorm is a warp reduction.
 // =========================================================================================
-template <typename T>
+template <typename T, int PER>
 __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, T* __restrict__ out, int B,
@@ -180,7 +180,6 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   }
   const int Hp = H >> 2, Wp = W >> 2;
   const int64_t nstrips = (int64_t)B * Tn * Hp;
-  const int per = C >> 5;  // channels per lane (C % 32 == 0, C <= 256)
   for (int64_t strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
     const int y = (int)(strip % Hp);
     const int64_t f = strip / Hp;  // frame index b*T + t
@@ -193,38 +192,75 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
       sin[i] = img[((((int64_t)b * Cin + ci) * Tn + t) * H + (4 * y + ky)) * W + xx];
     }
     __syncthreads();
-    for (int x = warp; x < Wp; x += nwarp) {
-      float acc[8];
+    // Register tile: a warp owns TT tokens (x = warp + nwarp * i) x `per` channels per lane, so that every staged
+    // input value and every weight is read from shared memory once per TT (resp. once per token tile) instead of
+    // once per FMA: the first version issued 4 LDS per 3 FMA and ran 20x off the HBM roofline (profiles/r01d).
+    constexpr int TT = 7;
+    for (int x0 = 0; x0 < Wp; x0 += TT * nwarp) {
+      float acc[TT][PER];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = (j < per) ? sb[lane + 32 * j] : 0.f;
-      for (int k = 0; k < K; ++k) {
-        const int ci = k >> 4, ky = (k >> 2) & 3, kx = k & 3;
-        const float xv = sin[(ci * 4 + ky) * W + 4 * x + kx];
-        const float* wr = wt + k * C + lane;
+      for (int i = 0; i < TT; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < per) acc[j] = fmaf(xv, wr[32 * j], acc[j]);
+        for (int j = 0; j < PER; ++j) acc[i][j] = sb[lane + 32 * j];
+      for (int k4 = 0; k4 < K; k4 += 4) {       // k4 = (ci, ky): the 4 kx taps are contiguous in the strip
+        const int rowi = k4 >> 2;
+        float wv[4][PER];
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+          for (int j = 0; j < PER; ++j) wv[kx][j] = wt[(k4 + kx) * C + lane + 32 * j];
+#pragma unroll
+        for (int i = 0; i < TT; ++i) {
+          const int x = x0 + warp + nwarp * i;
+          const float4 xv = x < Wp ? *reinterpret_cast<const float4*>(sin + rowi * W + 4 * x) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < PER; ++j) {
+            acc[i][j] = fmaf(xv.x, wv[0][j], acc[i][j]);
+            acc[i][j] = fmaf(xv.y, wv[1][j], acc[i][j]);
+            acc[i][j] = fmaf(xv.z, wv[2][j], acc[i][j]);
+            acc[i][j] = fmaf(xv.w, wv[3][j], acc[i][j]);
+          }
+        }
       }
-      float s = 0.f;
+      float mu[TT], rs[TT];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < per) s += acc[j];
-      const float mean = warp_sum(s) / (float)C;
-      float q = 0.f;
+      for (int i = 0; i < TT; ++i) {
+        float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < per) {
-          const float d = acc[j] - mean;
+        for (int j = 0; j < PER; ++j) sum += acc[i][j];
+        mu[i] = sum;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < TT; ++i) mu[i] += __shfl_xor_sync(0xffffffffu, mu[i], o);
+#pragma unroll
+      for (int i = 0; i < TT; ++i) {
+        mu[i] /= (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const float d = acc[i][j] - mu[i];
           q += d * d;
         }
-      const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
-      T* o = out + ((f * Hp + y) * (int64_t)Wp + x) * C;
+        rs[i] = q;
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < per) {
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < TT; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+#pragma unroll
+      for (int i = 0; i < TT; ++i) {
+        const int x = x0 + warp + nwarp * i;
+        if (x >= Wp) continue;
+        const float rstd = rsqrtf(rs[i] / (float)C + 1e-5f);
+        T* o = out + ((f * Hp + y) * (int64_t)Wp + x) * C;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
           const int c = lane + 32 * j;
-          st_f(o + c, (acc[j] - mean) * rstd * sb[C + c] + sb[2 * C + c]);
+          st_f(o + c, (acc[i][j] - mu[i]) * rstd * sb[C + c] + sb[2 * C + c]);
         }
+      }
     }
   }
 }
@@ -329,18 +365,34 @@ extern "C" int stgcma_patch_embed_fwd(const float* img, const float* w, const fl
   const size_t smem = sizeof(float) * ((size_t)Cin * 16 * C + 3 * C + (size_t)Cin * 4 * W);
   const int64_t strips = (int64_t)B * T * (H / 4);
   const int grid = (int)(strips < (int64_t)sm_count() * 4 ? strips : (int64_t)sm_count() * 4);
-  cudaError_t e;
+  STG_REQUIRE(W % 4 == 0 && ((uintptr_t)img & 15) == 0, "patch_embed_fwd: img must be 16-byte aligned");
+#define STG_PE_LAUNCH(T_, PER_)                                                                                          \
+  do {                                                                                                                   \
+    auto kern = patch_embed_kernel<T_, PER_>;                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
+    if (e != cudaSuccess) { set_error("patch_embed_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }   \
+    kern<<<grid, 256, smem, st>>>(img, w, bias, gamma, beta, (T_*)out, B, Cin, T, H, W, C);                               \
+  } while (0)
+#define STG_PE_DISPATCH(T_)                                      \
+  switch (C >> 5) {                                              \
+    case 1: STG_PE_LAUNCH(T_, 1); break;                         \
+    case 2: STG_PE_LAUNCH(T_, 2); break;                         \
+    case 3: STG_PE_LAUNCH(T_, 3); break;                         \
+    case 4: STG_PE_LAUNCH(T_, 4); break;                         \
+    case 5: STG_PE_LAUNCH(T_, 5); break;                         \
+    case 6: STG_PE_LAUNCH(T_, 6); break;                         \
+    case 7: STG_PE_LAUNCH(T_, 7); break;                         \
+    default: STG_PE_LAUNCH(T_, 8); break;                        \
+  }
   if (dtype == STGCMA_F32) {
-    e = cudaFuncSetAttribute(patch_embed_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("patch_embed_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
-    patch_embed_kernel<float><<<grid, 256, smem, st>>>(img, w, bias, gamma, beta, (float*)out, B, Cin, T, H, W, C);
+    STG_PE_DISPATCH(float);
   } else if (dtype == STGCMA_BF16) {
-    e = cudaFuncSetAttribute(patch_embed_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("patch_embed_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
-    patch_embed_kernel<bf16><<<grid, 256, smem, st>>>(img, w, bias, gamma, beta, (bf16*)out, B, Cin, T, H, W, C);
+    STG_PE_DISPATCH(bf16);
   } else {
     STG_REQUIRE(false, "patch_embed_fwd: bad dtype %d", dtype);
   }
+#undef STG_PE_DISPATCH
+#undef STG_PE_LAUNCH
   return check_launch("patch_embed_fwd");
 }
 

@@ -264,8 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform loop, one elected lane per instruction (mma_bf16_elect) =====================
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
@@ -283,12 +283,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ksteps > BK / 16) ksteps = BK / 16;
           for (int k = 0; k < ksteps; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in 16 B units
-            mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            mma_bf16_elect(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           }
-          mma_commit(smem_u32(empty + stage));
+          mma_commit_elect(smem_u32(empty + stage));
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(smem_u32(tfull + acc));
+        mma_commit_elect(smem_u32(tfull + acc));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
