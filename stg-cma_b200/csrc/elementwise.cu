@@ -126,9 +126,193 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TD* __restrict__ dy, 
   }
 }
 
+// -----------------------------------------------------------------------------------------
+// Row-in-registers variants (the ones the engine hits): LPR lanes own a row (32 / LPR rows per warp), each lane
+// holds VPL <= VMAX 4-element vectors, so x (and dy) are read from global memory exactly once and every lane of
+// the warp is busy for any C.  The warp-per-row kernels above kept 12 of 32 lanes busy at C = 96 and walked the
+// row three times: 26 % (fwd) / 52 % (bwd) of HBM peak (profiles/r01d).
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TX, typename TY, bool MERGE, int LPR, int VMAX>
+__global__ void __launch_bounds__(256) ln_fwd_rr_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, TY* __restrict__ y,
+                                                        float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                        int64_t rows, int C, int R, int vpl) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < rows;
+  RowAddr<MERGE> addr(ok ? row : 0, C, R);
+  float v[VMAX][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    if (i < vpl && ok) {
+      load4(x + addr.at(4 * (sub + LPR * i)), v[i]);
+      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    } else {
+      v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+    }
+  }
+  const float invC = 1.f / (float)C;
+  const float mean = group_sum<LPR>(s) * invC;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i)
+    if (i < vpl) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = v[i][e] - mean;
+        q += d * d;
+      }
+    }
+  const float rstd = rsqrtf(group_sum<LPR>(q) * invC + 1e-5f);
+  if (!ok) return;
+  TY* yrow = y + row * (int64_t)C;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i)
+    if (i < vpl) {
+      const int c = 4 * (sub + LPR * i);
+      float g[4], b[4], o[4];
+      load4(gamma + c, g);
+      load4(beta + c, b);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + b[e];
+      store4(yrow + c, o);
+    }
+  if (sub == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+template <typename TD, typename TX, typename TC, bool MERGE, int LPR, int VMAX>
+__global__ void __launch_bounds__(256) ln_bwd_rr_kernel(const TD* __restrict__ dy, const TX* __restrict__ x,
+                                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                        const float* __restrict__ gamma, const TX* dres, TX* dx,
+                                                        TC* __restrict__ dx_copy, int64_t rows, int C, int R, int vpl) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < rows;
+  RowAddr<MERGE> addr(ok ? row : 0, C, R);
+  const float mean = ok ? mean_in[row] : 0.f, rstd = ok ? rstd_in[row] : 0.f;
+  const TD* dyrow = dy + (ok ? row : 0) * (int64_t)C;
+  float gg[VMAX][4], xh[VMAX][4];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    if (i < vpl && ok) {
+      const int c = 4 * (sub + LPR * i);
+      float d4[4], x4[4], g4[4];
+      load4(dyrow + c, d4);
+      load4(x + addr.at(c), x4);
+      load4(gamma + c, g4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        gg[i][e] = d4[e] * g4[e];
+        xh[i][e] = (x4[e] - mean) * rstd;
+        s1 += gg[i][e];
+        s2 += gg[i][e] * xh[i][e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gg[i][e] = xh[i][e] = 0.f;
+    }
+  }
+  const float invC = 1.f / (float)C;
+  s1 = group_sum<LPR>(s1) * invC;
+  s2 = group_sum<LPR>(s2) * invC;
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i)
+    if (i < vpl) {
+      const int64_t off = addr.at(4 * (sub + LPR * i));
+      float o[4];
+      if (dres) {
+        // dres may alias dx: this lane reads its 4 elements before it writes them
+        float r4[4];
+        const TX* rp = dres + off;
+        if (sizeof(TX) == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(rp);
+          r4[0] = t.x; r4[1] = t.y; r4[2] = t.z; r4[3] = t.w;
+        } else {
+          const uint2 t = *reinterpret_cast<const uint2*>(rp);
+          r4[0] = __uint_as_float(t.x << 16); r4[1] = __uint_as_float(t.x & 0xffff0000u);
+          r4[2] = __uint_as_float(t.y << 16); r4[3] = __uint_as_float(t.y & 0xffff0000u);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = r4[e] + rstd * (gg[i][e] - s1 - xh[i][e] * s2);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rstd * (gg[i][e] - s1 - xh[i][e] * s2);
+      }
+      store4(dx + off, o);
+      if (dx_copy) store4(dx_copy + off, o);
+    }
+}
+
+// (LPR, VMAX) for a row of C channels; false when C does not fit the row-in-registers kernels
+static bool rr_config(int C, int& lpr, int& vpl, int& vmax) {
+  if (C % 4) return false;
+  const int per4 = C / 4;
+  lpr = per4 <= 32 ? 8 : (per4 <= 64 ? 16 : 32);
+  if (per4 % lpr) return false;
+  vpl = per4 / lpr;
+  if (vpl > 12) return false;
+  vmax = (vpl <= 4) ? 4 : 12;
+  if (vmax == 12 && lpr != 32) return false;
+  return true;
+}
+
+template <typename TX, typename TY, bool MERGE, int LPR, int VMAX>
+static void ln_fwd_rr_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                             int64_t rows, int C, int R, int vpl, cudaStream_t st) {
+  const int rpb = 8 * (32 / LPR);
+  ln_fwd_rr_kernel<TX, TY, MERGE, LPR, VMAX><<<(unsigned)ceil_div(rows, rpb), 256, 0, st>>>((const TX*)x, gamma, beta, (TY*)y, mean,
+                                                                                         rstd, rows, C, R, vpl);
+}
+
+template <typename TX, typename TY, bool MERGE>
+static bool ln_fwd_rr_dispatch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                               int64_t rows, int C, int R, cudaStream_t st) {
+  int lpr, vpl, vmax;
+  if (!rr_config(C, lpr, vpl, vmax)) return false;
+  if (vmax == 12) ln_fwd_rr_launch<TX, TY, MERGE, 32, 12>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
+  else if (lpr == 8) ln_fwd_rr_launch<TX, TY, MERGE, 8, 4>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
+  else if (lpr == 16) ln_fwd_rr_launch<TX, TY, MERGE, 16, 4>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
+  else ln_fwd_rr_launch<TX, TY, MERGE, 32, 4>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
+  return true;
+}
+
 template <typename TX, typename TY>
 static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                          int64_t rows, int C, int merge, int R, cudaStream_t st) {
+  if (merge ? ln_fwd_rr_dispatch<TX, TY, true>(x, gamma, beta, y, mean, rstd, rows, C, R, st)
+            : ln_fwd_rr_dispatch<TX, TY, false>(x, gamma, beta, y, mean, rstd, rows, C, R, st))
+    return check_launch("layernorm_fwd");
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div(rows, wpb)), block(wpb * 32);
   if (merge)
@@ -138,9 +322,32 @@ static int ln_fwd_launch(const void* x, const float* gamma, const float* beta, v
   return check_launch("layernorm_fwd");
 }
 
+template <typename TD, typename TX, typename TC, bool MERGE, int LPR, int VMAX>
+static void ln_bwd_rr_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                             const void* dres, void* dx, void* dx_copy, int64_t rows, int C, int R, int vpl, cudaStream_t st) {
+  const int rpb = 8 * (32 / LPR);
+  ln_bwd_rr_kernel<TD, TX, TC, MERGE, LPR, VMAX><<<(unsigned)ceil_div(rows, rpb), 256, 0, st>>>(
+      (const TD*)dy, (const TX*)x, mean, rstd, gamma, (const TX*)dres, (TX*)dx, (TC*)dx_copy, rows, C, R, vpl);
+}
+
+template <typename TD, typename TX, typename TC, bool MERGE>
+static bool ln_bwd_rr_dispatch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                               const void* dres, void* dx, void* dx_copy, int64_t rows, int C, int R, cudaStream_t st) {
+  int lpr, vpl, vmax;
+  if (!rr_config(C, lpr, vpl, vmax)) return false;
+  if (vmax == 12) ln_bwd_rr_launch<TD, TX, TC, MERGE, 32, 12>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
+  else if (lpr == 8) ln_bwd_rr_launch<TD, TX, TC, MERGE, 8, 4>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
+  else if (lpr == 16) ln_bwd_rr_launch<TD, TX, TC, MERGE, 16, 4>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
+  else ln_bwd_rr_launch<TD, TX, TC, MERGE, 32, 4>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
+  return true;
+}
+
 template <typename TD, typename TX, typename TC>
 static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                          const void* dres, void* dx, void* dx_copy, int64_t rows, int C, int merge, int R, cudaStream_t st) {
+  if (merge ? ln_bwd_rr_dispatch<TD, TX, TC, true>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, st)
+            : ln_bwd_rr_dispatch<TD, TX, TC, false>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, st))
+    return check_launch("layernorm_bwd");
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div(rows, wpb)), block(wpb * 32);
   if (merge)
