@@ -201,9 +201,10 @@ struct Params {
 // OCC: CTAs per SM the variant is compiled for.  OCC = 2 (BN <= 128, half the smem / TMEM each) is used for the
 // small-K, epilogue-bound shapes: two tiles in flight per SM hide the epilogue latency; OCC = 1 (BN <= 256) for the
 // large-K, tensor-bound ones (a 128 x 256 tile reads 25 % less shared memory per flop than two 128 x 128 tiles).
-template <int MODE, bool OUT_F32, int NRES, int OCC>
+template <int MODE, bool OUT_F32, int NRES, int OCC, bool TMAOUT>
 __global__ void __launch_bounds__(kThreads, OCC)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmC, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for SWIZZLE_128B, by pointer arithmetic on the shared pointer (keeps ld/st.shared addressing)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -301,6 +302,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* stg = staging + (size_t)(warp - 2) * 32 * kStageRowF;
     const EpiParams ep = p.epi;
     uint32_t acc = 0, acc_phase = 0;
+    if (TMAOUT) {
+      // Plain bf16 output (out = acc + bias): the tile is written lane-per-row, straight from the TMEM load, into a
+      // K-major SWIZZLE_128B staging tile and leaves with one TMA store per 64 columns -- ~2 instructions per element
+      // instead of ~17 through the transposing epilogue below, which was issue-bound at K = 96 (ncu: 51 % issue
+      // slots busy, 41 % DRAM throughput; profiles/r01e).  Row / column tails are clipped by the tensor map.
+      uint8_t* stile = reinterpret_cast<uint8_t*>(staging);
+      const int trow = q * 32 + lane;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const int g = mt / p.m_tiles_g;
+        const int m_blk = mt - g * p.m_tiles_g;
+        const uint32_t t_row = tmem_base + acc * (uint32_t)p.BN + ((uint32_t)(q * 32) << 16);
+        mbar_wait(smem_u32(tfull + acc), acc_phase);
+        tc_fence_after();
+        // the previous tile's TMA store must have finished READING the staging tile
+        if (!first) {
+          if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        }
+        first = false;
+        for (int ch = par; ch < nchunks; ch += 2) {
+          const int c0 = ch << 5;
+          const bool wide = p.BN - c0 >= 32;
+          float v[32];
+          if (wide) tmem_ld32(t_row + (uint32_t)c0, v);
+          else tmem_ld16(t_row + (uint32_t)c0, v);
+          const int col = n_blk * p.BN + c0;
+          const float* bp = ep.bias ? ep.bias + (int64_t)g * p.N + col : nullptr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j >= 2 && !wide) break;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = v[8 * j + i];
+            if (bp && col + 8 * j < p.N) {   // N % 8 == 0: an 8-column group is inside or outside as a whole
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + 8 * j)), b1 = __ldg(reinterpret_cast<const float4*>(bp + 8 * j + 4));
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            const int cc = c0 + 8 * j;
+            Vec<bf16> pk;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk.v[i] = o[i];
+            pk.store(reinterpret_cast<bf16*>(stile + (cc >> 6) * kABytes + trow * 128 + ((((cc & 63) >> 3) ^ (trow & 7)) << 4)));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty + acc));   // accumulator drained: the MMA warp may reuse it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (warp == 2 && lane == 0) {
+          for (int cb = 0; cb * 64 < p.BN; ++cb) {
+            if (n_blk * p.BN + cb * 64 >= p.N) break;
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(stile + cb * kABytes)), "r"(n_blk * p.BN + cb * 64),
+                           "r"(m_blk * BM), "r"(g)
+                         : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
@@ -397,6 +465,10 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
     const int64_t cost = ceil_div(N, bn) * (int64_t)bn + (bn < 64 && N > bn ? N : 0);   // avoid slivers when N is large
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
   }
+  // Plain bf16 output -> TMA-store epilogue.  Its 64-column store boxes are clipped only at the tensor's edge, so
+  // either the whole N fits one tile or the tile width is a multiple of 64 (and <= 128: two staging blocks).
+  // (Forcing BN = 128 for N = 288 to qualify was slower than BN = 96 with the transposing epilogue: measured.)
+  const bool tma_cand = ep.mode == STGCMA_EPI_LINEAR && !ep.out_f32 && !ep.res1 && !ep.res2 && !ep.rowscale;
   p.BN = best_bn;
   p.n_tiles = (int)ceil_div(N, p.BN);
   p.m_tiles_g = (int)ceil_div(p.group_rows, BM);
@@ -416,11 +488,18 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   p.tmem_cols = cols;
   p.epi = ep;
 
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmC;
   int rc = make_map(&tmA, A, p.group_rows, K, lda, groups, BM);
   if (rc) return rc;
   rc = make_map(&tmW, W, N, K, ldw, groups, p.BN);
   if (rc) return rc;
+  // plain bf16 output -> TMA-store epilogue (needs the two-block staging tile: BN <= 128)
+  const bool tma_out = tma_cand && p.BN <= 128 && (p.n_tiles == 1 || p.BN % 64 == 0);
+  tmC = tmA;
+  if (tma_out) {
+    rc = make_map(&tmC, ep.out, p.group_rows, N, ep.ldo, groups, BM);
+    if (rc) return rc;
+  }
 
   const size_t smem = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 256;
   const int grid = p.num_tiles < occ * sm_count() ? p.num_tiles : occ * sm_count();
@@ -431,12 +510,12 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   }
 #define STG_TC_LAUNCH(MODE_, F32_, NRES_)                                                                      \
   do {                                                                                                         \
-    if (occ == 1) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 1);                                                       \
-    STG_TC_LAUNCH2(MODE_, F32_, NRES_, 2);                                                                     \
+    if (occ == 1) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 1, false);                                                \
+    STG_TC_LAUNCH2(MODE_, F32_, NRES_, 2, false);                                                              \
   } while (0)
-#define STG_TC_LAUNCH2(MODE_, F32_, NRES_, OCC_)                                                               \
+#define STG_TC_LAUNCH2(MODE_, F32_, NRES_, OCC_, TMA_)                                                         \
   do {                                                                                                         \
-    auto kern = gemm_tc_kernel<MODE_, F32_, NRES_, OCC_>;                                                      \
+    auto kern = gemm_tc_kernel<MODE_, F32_, NRES_, OCC_, TMA_>;                                                    \
     static std::once_flag once;                                                                                \
     static cudaError_t attr_err = cudaSuccess;                                                                 \
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCC_ == 1 ? 232448 : 115712); }); \
@@ -444,10 +523,14 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
       set_error("gemm: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));                    \
       return STGCMA_ECUDA;                                                                                     \
     }                                                                                                          \
-    kern<<<grid, kThreads, smem, st>>>(tmA, tmW, p);                                                           \
+    kern<<<grid, kThreads, smem, st>>>(tmA, tmW, tmC, p);                                                         \
     return check_launch("gemm(tcgen05)");                                                                      \
   } while (0)
   const bool f32 = ep.out_f32 != 0;
+  if (tma_out) {
+    if (occ == 1) STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 1, true);
+    STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 2, true);
+  }
   switch (ep.mode) {
     case STGCMA_EPI_LINEAR:
       if (f32) {
