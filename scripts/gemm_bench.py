@@ -23,6 +23,12 @@ SHAPES = [  # M, N, K, groups, epi, opts
     (62720, 1152, 384, 1, lib.EPI_LINEAR, dict(bias=True)),
     (15680, 768, 3072, 1, lib.EPI_LINEAR, dict(bias=True)),
     (8192, 8192, 8192, 1, lib.EPI_LINEAR, dict()),
+    (31360, 2304, 768, 1, lib.EPI_LINEAR, dict(bias=True)),
+    (31360, 1152, 768, 1, lib.EPI_LINEAR, dict(bias=True)),
+    (31360, 768, 768, 1, lib.EPI_LINEAR, dict(bias=True)),
+    (3920, 2304, 768, 1, lib.EPI_LINEAR, dict(bias=True)),
+    (31360, 2304, 384, 1, lib.EPI_LINEAR, dict(bias=True)),
+    (31360, 2304, 768, 1, lib.EPI_GELU, dict(bias=True, out_pre=True)),
 ]
 
 
@@ -66,11 +72,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", type=int, default=-1)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--from", dest="first", type=int, default=0)
     args = ap.parse_args()
     if args.only >= 0:
         run(args.only, 2, 1)
         return
-    for i in range(len(SHAPES)):
+    for i in range(args.first, len(SHAPES)):
         M, N, K = SHAPES[i][:3]
         sets = max(1, min(6, int(3e8 // (M * (N + K) * 2)) + 1))   # rotate operand sets when one set fits in L2
         run(i, args.reps, sets)

@@ -64,17 +64,19 @@ def main():
     torch.cuda.synchronize()
     agg = OrderedDict()
     for key, e0, e1, fl, nb in rec:
-        d = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
+        d = agg.setdefault(key, [0, 0.0, 0.0, 0.0, 1e9, 0.0])
+        ms = e0.elapsed_time(e1)
         d[0] += 1
-        d[1] += e0.elapsed_time(e1)
+        d[1] += ms
+        d[4], d[5] = min(d[4], ms), max(d[5], ms)
         d[2] += fl
         d[3] += nb
     tot = sum(d[1] for d in agg.values())
     print(f"batch {args.batch}: {len(rec)} calls, {tot:.2f} ms total")
-    print("| kind | dtype | M | N(Ka) | K(Nb) | g | epi | flags | calls | ms | TFLOP/s | GB/s |")
-    print("|---|---|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|")
+    print("| kind | dtype | M | N(Ka) | K(Nb) | g | epi | flags | calls | ms | TFLOP/s | GB/s | min us | max us |")
+    print("|---|---|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|---:|---:|")
     for key, d in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print("| " + " | ".join(str(k) for k in key) + f" | {d[0]} | {d[1]:.3f} | {d[2] / d[1] / 1e9:.1f} | {d[3] / d[1] / 1e6:.0f} |")
+        print("| " + " | ".join(str(k) for k in key) + f" | {d[0]} | {d[1]:.3f} | {d[2] / d[1] / 1e9:.1f} | {d[3] / d[1] / 1e6:.0f} | {d[4] * 1e3:.0f} | {d[5] * 1e3:.0f} |")
 
 
 if __name__ == "__main__":

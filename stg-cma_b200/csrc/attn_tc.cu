@@ -56,23 +56,32 @@ __device__ __forceinline__ void gather_async(uint8_t* tile, const bf16* __restri
   }
 }
 
+// Per-lane column metadata of the 14 score columns a lane owns (c = i*8 + 2t + e), head independent and hoisted out of
+// the head loops: rowoff(c) | region(c) << 8, or -1 for pad columns.  coloff(c) = K0 - rowoff(c), K0 = (ws-1)*(2ws-1)+ws-1.
+__device__ __forceinline__ void col_meta(int (&cm)[14], const Win& w, int N, int t) {
+#pragma unroll
+  for (int i = 0; i < 7; ++i)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = i * 8 + 2 * t + e;
+      cm[2 * i + e] = c < N ? ((int)w.rowoff[c] | ((int)w.reg[c] << 8)) : -1;
+    }
+}
+
 // s (7 n-tiles of a 16 x 56 block, raw q.k accumulators) -> log2-domain logits with bias and mask applied.
-// `rowo[2]`: bias row offsets of this thread's two rows; columns use `colo` from the Win tables.
 // ROWS_ARE_QUERIES: idx = rowoff(row) + coloff(col); else idx = rowoff(col) + coloff(row) (transposed scores).
+// oa / ob: bias offsets of this thread's two rows (rowoff resp. coloff), ga / gb their mask regions.
 template <bool ROWS_ARE_QUERIES>
-__device__ __forceinline__ void apply_bias_mask(float (&s)[7][4], const float* __restrict__ tbl, const Win& w, int row_a,
-                                                int row_b, int N, int t, bool shifted) {
-  const int ra = row_a < N ? row_a : 0, rb = row_b < N ? row_b : 0;
-  const int oa = ROWS_ARE_QUERIES ? w.rowoff[ra] : w.coloff[ra], ob = ROWS_ARE_QUERIES ? w.rowoff[rb] : w.coloff[rb];
-  const int ga = w.reg[ra], gb = w.reg[rb];
+__device__ __forceinline__ void apply_bias_mask(float (&s)[7][4], const float* __restrict__ tbl, const int (&cm)[14], int oa,
+                                                int ob, int ga, int gb, int K0, bool shifted) {
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int c = i * 8 + 2 * t + e;
-      if (c < N) {
-        const int oc = ROWS_ARE_QUERIES ? w.coloff[c] : w.rowoff[c];
-        const int gc = w.reg[c];
+      const int m = cm[2 * i + e];
+      if (m >= 0) {
+        const int oc = ROWS_ARE_QUERIES ? K0 - (m & 255) : (m & 255);
+        const int gc = m >> 8;
         float va = s[i][e] * kScale + tbl[oa + oc];
         float vb = s[i][2 + e] * kScale + tbl[ob + oc];
         if (shifted) {
@@ -86,6 +95,32 @@ __device__ __forceinline__ void apply_bias_mask(float (&s)[7][4], const float* _
         s[i][2 + e] = -INFINITY;
       }
     }
+  }
+}
+
+// write this lane's part of a 16 x 32 fp32 accumulator block (rows ra / rb of the tile, head h) as bf16 into a
+// [NP][LD] shared tile (the warp's own rows: conflict-free, see the LD padding)
+__device__ __forceinline__ void stage_rows(uint8_t* tile, int LD, const float (&o)[4][4], float sa, float sb, int ra, int rb,
+                                           int h, int t) {
+  uint8_t* pa = tile + ra * LD + (h * HD + 2 * t) * 2;
+  uint8_t* pb = tile + rb * LD + (h * HD + 2 * t) * 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    *reinterpret_cast<uint32_t*>(pa + i * 16) = pack_bf16(o[i][0] * sa, o[i][1] * sa);
+    *reinterpret_cast<uint32_t*>(pb + i * 16) = pack_bf16(o[i][2] * sb, o[i][3] * sb);
+  }
+}
+
+// coalesced scatter of a staged [N rows][HG*32] tile to the token-major destination (16 B per lane, a row's HG*64 B
+// segment is contiguous in global memory)
+template <int HG>
+__device__ __forceinline__ void scatter_rows(const uint8_t* tile, bf16* __restrict__ dst, int64_t frame_row0, int64_t ld_g,
+                                             int col0, const Win& w, int N, int tid) {
+  constexpr int CH = HG * 4, LD = HG * 64 + 16;
+  for (int e = tid; e < N * CH; e += NTH) {
+    const int r = e / CH, c = e - r * CH;
+    const uint4 v = *reinterpret_cast<const uint4*>(tile + r * LD + c * 16);
+    *reinterpret_cast<uint4*>(dst + (frame_row0 + w.tok[r]) * ld_g + col0 + c * 8) = v;
   }
 }
 
@@ -152,25 +187,30 @@ __global__ void __launch_bounds__(NTH) window_fwd_kernel(const bf16* __restrict_
   const int wy = wi / nwr, wx = wi - wy * nwr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   win_setup(w, wy, wx, ws, shift, R, N, tid);
-  for (int e = tid; e < HG * T2; e += NTH) {
-    const int hh = e / T2, i = e - hh * T2;
-    tbl[e] = i < T2v ? rpb[(int64_t)i * heads + hg * HG + hh] : 0.f;
-  }
   __syncthreads();
   const int64_t row0 = frame * L;
   gather_async<HG>(tq, qkv, row0, 3 * C, hg * HG * HD, w, N, tid);
   gather_async<HG>(tk, qkv, row0, 3 * C, C + hg * HG * HD, w, N, tid);
   gather_async<HG>(tv, qkv, row0, 3 * C, 2 * C + hg * HG * HD, w, N, tid);
   cp_async_commit();
+  for (int e = tid; e < HG * T2; e += NTH) {   // overlaps the gather
+    const int hh = e / T2, i = e - hh * T2;
+    tbl[e] = i < T2v ? __ldg(rpb + (int64_t)i * heads + hg * HG + hh) : 0.f;
+  }
+  const int ra = warp * 16 + g, rb = ra + 8;
+  const int K0 = (ws - 1) * (2 * ws - 1) + (ws - 1);
+  int cm[14];
+  col_meta(cm, w, N, t);
+  const int rav = ra < N ? ra : 0, rbv = rb < N ? rb : 0;
+  const int oa = w.rowoff[rav], ob = w.rowoff[rbv], ga = w.reg[rav], gb = w.reg[rbv];
   cp_async_wait<0>();
   __syncthreads();
 
-  const int ra = warp * 16 + g, rb = ra + 8;
 #pragma unroll 1
   for (int h = 0; h < HG; ++h) {
     float s[7][4];
     scores(s, tq, tk, LD, warp, h, lane);
-    apply_bias_mask<true>(s, tbl + h * T2, w, ra, rb, N, t, shift > 0);
+    apply_bias_mask<true>(s, tbl + h * T2, cm, oa, ob, ga, gb, K0, shift > 0);
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
@@ -194,18 +234,12 @@ __global__ void __launch_bounds__(NTH) window_fwd_kernel(const bf16* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     pv(o, s, tv, LD, h, lane);
-    const int col0 = (hg * HG + h) * HD + 2 * t;
-    if (ra < N) {
-      bf16* dst = out + (row0 + w.tok[ra]) * C + col0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t*>(dst + i * 8) = pack_bf16(o[i][0] * inv0, o[i][1] * inv0);
-    }
-    if (rb < N) {
-      bf16* dst = out + (row0 + w.tok[rb]) * C + col0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t*>(dst + i * 8) = pack_bf16(o[i][2] * inv1, o[i][3] * inv1);
-    }
+    // q rows of this warp / head are dead (only this warp read them): they stage the output
+    __syncwarp();
+    stage_rows(tq, LD, o, inv0, inv1, ra, rb, h, t);
   }
+  __syncthreads();
+  scatter_rows<HG>(tq, out, row0, C, hg * HG * HD, w, N, tid);
 }
 
 template <int HG>
@@ -218,7 +252,8 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
   uint8_t* tk = tq + NP * LD;
   uint8_t* tv = tk + NP * LD;
   uint8_t* td = tv + NP * LD;
-  float* tbl = reinterpret_cast<float*>(td + NP * LD);   // [HG][T2]
+  uint8_t* tdq = td + NP * LD;                           // dq staging (path A output; q itself is still needed by path B)
+  float* tbl = reinterpret_cast<float*>(tdq + NP * LD);  // [HG][T2]
   const int T2 = ((2 * ws - 1) * (2 * ws - 1) + 3) & ~3;
   const int T2v = (2 * ws - 1) * (2 * ws - 1);
   float* s_lse = tbl + HG * T2;                          // [HG][NP]  log2-domain logsumexp per query row (+inf on pad rows)
@@ -232,10 +267,6 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
   const int wy = wi / nwr, wx = wi - wy * nwr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   win_setup(w, wy, wx, ws, shift, R, N, tid);
-  for (int e = tid; e < HG * T2; e += NTH) {
-    const int hh = e / T2, i = e - hh * T2;
-    tbl[e] = i < T2v ? rpb[(int64_t)i * heads + hg * HG + hh] : 0.f;
-  }
   __syncthreads();
   const int64_t row0 = frame * L;
   gather_async<HG>(tq, qkv, row0, 3 * C, hg * HG * HD, w, N, tid);
@@ -243,16 +274,25 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
   gather_async<HG>(tv, qkv, row0, 3 * C, 2 * C + hg * HG * HD, w, N, tid);
   gather_async<HG>(td, dout, row0, C, hg * HG * HD, w, N, tid);
   cp_async_commit();
+  for (int e = tid; e < HG * T2; e += NTH) {   // overlaps the gather
+    const int hh = e / T2, i = e - hh * T2;
+    tbl[e] = i < T2v ? __ldg(rpb + (int64_t)i * heads + hg * HG + hh) : 0.f;
+  }
+  const int ra = warp * 16 + g, rb = ra + 8;
+  const int K0 = (ws - 1) * (2 * ws - 1) + (ws - 1);
+  int cm[14];
+  col_meta(cm, w, N, t);
+  const int rav = ra < N ? ra : 0, rbv = rb < N ? rb : 0;
+  const int roa = w.rowoff[rav], rob = w.rowoff[rbv], ga = w.reg[rav], gb = w.reg[rbv];
   cp_async_wait<0>();
   __syncthreads();
 
-  const int ra = warp * 16 + g, rb = ra + 8;
   // ---------------- path A: this warp's rows are queries ----------------
 #pragma unroll 1
   for (int h = 0; h < HG; ++h) {
     float s[7][4], dp[7][4];
     scores(s, tq, tk, LD, warp, h, lane);
-    apply_bias_mask<true>(s, tbl + h * T2, w, ra, rb, N, t, shift > 0);
+    apply_bias_mask<true>(s, tbl + h * T2, cm, roa, rob, ga, gb, K0, shift > 0);
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
@@ -299,25 +339,16 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     pv(o, s, tk, LD, h, lane);               // dq = dS . k
-    const int col0 = (hg * HG + h) * HD + 2 * t;
-    if (ra < N) {
-      bf16* dst = dqkv + (row0 + w.tok[ra]) * 3 * C + col0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t*>(dst + i * 8) = pack_bf16(o[i][0] * kScale, o[i][1] * kScale);
-    }
-    if (rb < N) {
-      bf16* dst = dqkv + (row0 + w.tok[rb]) * 3 * C + col0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t*>(dst + i * 8) = pack_bf16(o[i][2] * kScale, o[i][3] * kScale);
-    }
+    stage_rows(tdq, LD, o, kScale, kScale, ra, rb, h, t);
   }
   __syncthreads();
   // ---------------- path B: this warp's rows are keys; columns are queries ----------------
+  const int coa = K0 - roa, cob = K0 - rob;
 #pragma unroll 1
   for (int h = 0; h < HG; ++h) {
     float s[7][4], dp[7][4];
     scores(s, tk, tq, LD, warp, h, lane);    // S^T = k . q^T
-    apply_bias_mask<false>(s, tbl + h * T2, w, ra, rb, N, t, shift > 0);
+    apply_bias_mask<false>(s, tbl + h * T2, cm, coa, cob, ga, gb, K0, shift > 0);
     scores(dp, tv, td, LD, warp, h, lane);   // dP^T = v . dO^T
     const float* lse_h = s_lse + h * NP;
     const float* del_h = s_delta + h * NP;
@@ -340,29 +371,20 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
     }
     pv(ok, dp, tq, LD, h, lane);             // dk = dS^T . q
     pv(ov, s, td, LD, h, lane);              // dv = P^T . dO
-    const int col0 = (hg * HG + h) * HD + 2 * t;
-    if (ra < N) {
-      bf16* dst = dqkv + (row0 + w.tok[ra]) * 3 * C + col0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<uint32_t*>(dst + C + i * 8) = pack_bf16(ok[i][0] * kScale, ok[i][1] * kScale);
-        *reinterpret_cast<uint32_t*>(dst + 2 * C + i * 8) = pack_bf16(ov[i][0], ov[i][1]);
-      }
-    }
-    if (rb < N) {
-      bf16* dst = dqkv + (row0 + w.tok[rb]) * 3 * C + col0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<uint32_t*>(dst + C + i * 8) = pack_bf16(ok[i][2] * kScale, ok[i][3] * kScale);
-        *reinterpret_cast<uint32_t*>(dst + 2 * C + i * 8) = pack_bf16(ov[i][2], ov[i][3]);
-      }
-    }
+    // k / v rows of this warp / head are dead now (path B reads them only as this warp's A operand; path A, which
+    // read every row, is complete for all warps): they stage dk / dv
+    __syncwarp();
+    stage_rows(tk, LD, ok, kScale, kScale, ra, rb, h, t);
+    stage_rows(tv, LD, ov, 1.f, 1.f, ra, rb, h, t);
   }
+  __syncthreads();
+  scatter_rows<HG>(tdq, dqkv, row0, 3 * C, hg * HG * HD, w, N, tid);
+  scatter_rows<HG>(tk, dqkv, row0, 3 * C, C + hg * HG * HD, w, N, tid);
+  scatter_rows<HG>(tv, dqkv, row0, 3 * C, 2 * C + hg * HG * HD, w, N, tid);
 }
 
 static int pick_hg(int heads) {
-  if (heads % 4 == 0) return 4;
-  if (heads % 3 == 0) return 3;
+  if (heads % 3 == 0) return 3;   // HG = 4 would need 88 KB in the backward (5 tiles): 2 CTAs per SM instead of 3
   if (heads % 2 == 0) return 2;
   return 1;
 }
@@ -386,7 +408,7 @@ static int bwd_launch(const void* qkv, const float* rpb, const void* dout, void*
                       int heads, cudaStream_t st) {
   constexpr int LD = HG * 64 + 16;
   const int T2 = ((2 * ws - 1) * (2 * ws - 1) + 3) & ~3;
-  const size_t smem = (size_t)4 * NP * LD + sizeof(float) * (HG * T2 + 2 * HG * NP) + sizeof(Win);
+  const size_t smem = (size_t)5 * NP * LD + sizeof(float) * (HG * T2 + 2 * HG * NP) + sizeof(Win);
   auto kern = window_bwd_kernel<HG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("window_attn_bwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
@@ -400,7 +422,6 @@ static int bwd_launch(const void* qkv, const float* rpb, const void* dout, void*
 int window_attn_fwd_bf16(const void* qkv, const float* rpb, void* out, int64_t frames, int R, int ws, int shift, int heads,
                          cudaStream_t st) {
   switch (wtc::pick_hg(heads)) {
-    case 4: return wtc::fwd_launch<4>(qkv, rpb, out, frames, R, ws, shift, heads, st);
     case 3: return wtc::fwd_launch<3>(qkv, rpb, out, frames, R, ws, shift, heads, st);
     case 2: return wtc::fwd_launch<2>(qkv, rpb, out, frames, R, ws, shift, heads, st);
     default: return wtc::fwd_launch<1>(qkv, rpb, out, frames, R, ws, shift, heads, st);
@@ -410,7 +431,6 @@ int window_attn_fwd_bf16(const void* qkv, const float* rpb, void* out, int64_t f
 int window_attn_bwd_bf16(const void* qkv, const float* rpb, const void* dout, void* dqkv, int64_t frames, int R, int ws,
                          int shift, int heads, cudaStream_t st) {
   switch (wtc::pick_hg(heads)) {
-    case 4: return wtc::bwd_launch<4>(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads, st);
     case 3: return wtc::bwd_launch<3>(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads, st);
     case 2: return wtc::bwd_launch<2>(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads, st);
     default: return wtc::bwd_launch<1>(qkv, rpb, dout, dqkv, frames, R, ws, shift, heads, st);

@@ -647,8 +647,8 @@ static int gemm_tn_launch(const void* A, const void* B, const float* rowscale, f
 }
 
 // bf16 tensor-core version (gemm_tn_tc.cu); -1 = arguments do not fit it
-int gemm_tn_bf16(const void* A, const void* B, float* dW, float* csumA, int64_t M, int Ka, int Nb, int64_t lda, int64_t ldb,
-                 int64_t ldo, cudaStream_t st);
+int gemm_tn_bf16(const void* A, const void* B, const float* rowscale, float* dW, float* csumA, int64_t M, int Ka, int Nb,
+                 int64_t lda, int64_t ldb, int64_t ldo, cudaStream_t st);
 
 }  // namespace stgcma
 
@@ -693,8 +693,8 @@ extern "C" int stgcma_gemm_tn(const void* A, const void* B, const float* rowscal
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == STGCMA_F32) return gemm_tn_launch<float>(A, B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb, ldo, st);
   if (dtype == STGCMA_BF16) {
-    if (!rowscale && !csumB) {
-      const int rc = gemm_tn_bf16(A, B, dW, csumA, M, Ka, Nb, lda, ldb, ldo, st);
+    if (!csumB) {
+      const int rc = gemm_tn_bf16(A, B, rowscale, dW, csumA, M, Ka, Nb, lda, ldb, ldo, st);
       if (rc != -1) return rc;
     }
     return gemm_tn_launch<bf16>(A, B, rowscale, dW, csumA, csumB, M, Ka, Nb, lda, ldb, ldo, st);
