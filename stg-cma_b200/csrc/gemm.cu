@@ -646,6 +646,9 @@ static int gemm_tn_launch(const void* A, const void* B, const float* rowscale, f
   return check_launch("gemm_tn");
 }
 
+// skinny-K residual GEMM (gemm_skinny.cu); -1 = not such a call
+int gemm_skinny_bf16(const void* A, const void* W, int64_t M, int N, int K, int64_t lda, int64_t ldw, int groups,
+                     const EpiParams& ep, cudaStream_t st);
 // bf16 tensor-core version (gemm_tn_tc.cu); -1 = arguments do not fit it
 int gemm_tn_bf16(const void* A, const void* B, const float* rowscale, float* dW, float* csumA, int64_t M, int Ka, int Nb,
                  int64_t lda, int64_t ldb, int64_t ldo, cudaStream_t st);
@@ -683,6 +686,10 @@ extern "C" int stgcma_gemm(const void* A, const void* W, const float* bias, cons
                   ((uintptr_t)res1 & 15) == 0 && ((uintptr_t)res2 & 15) == 0 && ((uintptr_t)aux & 15) == 0 &&
                   ((uintptr_t)out_pre & 15) == 0 && ((uintptr_t)bias & 15) == 0,
               "gemm(bf16): operands must be 16-byte aligned");
+  if (ep.res1 && K <= 128) {   // adapter up-projection + residual adds: an HBM stream, not a tensor-core problem
+    const int rc = gemm_skinny_bf16(A, W, M, N, K, lda, ldw, groups, ep, st);
+    if (rc != -1) return rc;
+  }
   return tc::launch(A, W, M, N, K, lda, ldw, groups, ep, st);
 }
 

@@ -51,6 +51,13 @@ GEMM_CASES = [
     (20, 32, 512, 1, R.EPI_LINEAR, dict(bias=True)),
     (640, 768, 3072, 1, R.EPI_LINEAR, dict(bias=True, res1=True)),    # mlp.fc2 at stage 3: 48 k-blocks
     (50000, 288, 96, 1, R.EPI_LINEAR, dict(bias=True)),               # many tiles per CTA (persistent loop, phases)
+    # skinny-K residual GEMMs (gemm_skinny.cu): adapter D_fc2 + residual adds into the fp32 stream, and the dX of D_fc1
+    (2 * 147, 96, 16, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, f32=True)),     # ragged 16-row slabs per group
+    (2 * 1000, 384, 32, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, f32=True)),
+    (2 * 333, 768, 48, 2, R.EPI_LINEAR, dict(bias=True, res1=True, f32=True, rowscale=True)),
+    (2 * 100, 128, 16, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True)),              # N % 48 != 0: 64-column blocks
+    (2 * 130, 192, 96, 2, R.EPI_LINEAR, dict(res1=True)),                                    # Swin-L adapter width, 6 k-steps
+    (2 * 40000, 96, 16, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, rowscale=True, f32=True)),
 ]
 
 
@@ -61,11 +68,12 @@ def test_gemm(case, dtype):
     A = rnd(M, K, dtype=dtype, seed=1)
     W = rnd(groups, N, K, dtype=dtype, seed=2, scale=K ** -0.5)
     bias = rnd(groups, N, dtype=torch.float32, seed=3) if o.get("bias") else None
-    res1 = rnd(M, N, dtype=dtype, seed=4) if o.get("res1") else None
+    odt = torch.float32 if o.get("f32") else dtype     # fp32 residual stream: out and res1 are fp32 whatever the activation dtype
+    res1 = rnd(M, N, dtype=odt, seed=4) if o.get("res1") else None
     res2 = rnd(M, N, dtype=dtype, seed=5) if o.get("res2") else None
     rowscale = (torch.rand(M, generator=torch.Generator().manual_seed(6)) * 2).cuda() if o.get("rowscale") else None
     aux = rnd(M, N, dtype=dtype, seed=7) if o.get("aux") else None
-    out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
+    out = torch.full((M, N), float("nan"), dtype=odt, device="cuda")
     out_pre = torch.full((M, N), float("nan"), dtype=dtype, device="cuda") if o.get("out_pre") else None
     L().gemm(A, W, out, M, N, K, bias=bias, res1=res1, res2=res2, rowscale=rowscale, aux=aux, out_pre=out_pre,
              groups=groups, epi=epi)
