@@ -9,6 +9,7 @@
 //   backward: path A (warp = query rows)  recompute P, dP = dO v^T, delta = rowsum(P dP), dq = scale dS k
 //             path B (warp = key rows)    recompute P^T with the saved row statistics, dk = scale dS^T q, dv = P^T dO
 //             (recomputing the 49 x 49 scores transposed is cheaper than transposing register fragments)
+#include <stdlib.h>
 #include "mma.cuh"
 
 namespace stgcma {
@@ -384,6 +385,8 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
 }
 
 static int pick_hg(int heads) {
+  static const int force = getenv("STGCMA_WIN_HG") ? atoi(getenv("STGCMA_WIN_HG")) : 0;   // tuning knob
+  if (force > 0 && heads % force == 0) return force;
   if (heads % 3 == 0) return 3;   // HG = 4 would need 88 KB in the backward (5 tiles): 2 CTAs per SM instead of 3
   if (heads % 2 == 0) return 2;
   return 1;
