@@ -199,7 +199,13 @@ __global__ void __launch_bounds__(256) tt_fwd_kernel(const bf16* __restrict__ qk
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tt_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ tbl,
+// FIXED_HEAD: the block has a multiple of `heads` warps and warp w always works on head w % heads, so the bias-table
+// gradient dS is summed element-wise in REGISTERS over the CTA's whole life (per modality) and folded into the
+// diagonals once at the end.  The generic variant adds every dS element to its diagonal in shared memory as it goes:
+// fp32 shared atomics are CAS loops and the ~10 elements of a diagonal collide inside the warp (ncu, profiles/r01f:
+// 7 retries per atomic, ~25 % of the kernel's instructions).
+template <bool FIXED_HEAD, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) tt_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ tbl,
                                                      const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
                                                      float* __restrict__ dtbl, int G, int B, Geo geo) {
   extern __shared__ __align__(16) uint8_t tsm[];
@@ -210,10 +216,18 @@ __global__ void __launch_bounds__(256) tt_bwd_kernel(const bf16* __restrict__ qk
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   const int T = geo.T, L = geo.L, NT = geo.NT, heads = geo.heads;
   const int nb = 2 * T - 1;
-  for (int i = tid; i < G * nb * heads; i += 256) {
+  const int nthr = blockDim.x, nwarp = nthr >> 5;
+  for (int i = tid; i < G * nb * heads; i += nthr) {
     tb_s[i] = tbl[i];
     db_s[i] = 0.f;
   }
+  float dsacc[2][2][4];   // [modality][n-tile][e]   (FIXED_HEAD)
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) dsacc[a][i][0] = dsacc[a][i][1] = dsacc[a][i][2] = dsacc[a][i][3] = 0.f;
+  const int task0 = FIXED_HEAD ? (warp / heads) * heads + (warp % heads) : warp;   // == warp; kept explicit
+  const int task_stride = nwarp;   // FIXED_HEAD: a multiple of heads, so task % heads never changes
   const int tiles_per_seq = (L + NT - 1) / NT;
   const int64_t ntiles = (int64_t)G * B * tiles_per_seq;
   for (int64_t tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
@@ -222,12 +236,12 @@ __global__ void __launch_bounds__(256) tt_bwd_kernel(const bf16* __restrict__ qk
     const int nt = (L - n0) < NT ? (L - n0) : NT;
     const int64_t row0 = ((int64_t)g * B + b) * T * L + n0;
     __syncthreads();
-    copy_tile<true>(tile, geo.ts3, (uint8_t*)(qkv + row0 * 3 * geo.C), (int64_t)L * geo.row3, geo.row3, nt, T, tid, 256);
-    copy_tile<true>(dtile, geo.ts1, (uint8_t*)(dout + row0 * geo.C), (int64_t)L * geo.row1, geo.row1, nt, T, tid, 256);
+    copy_tile<true>(tile, geo.ts3, (uint8_t*)(qkv + row0 * 3 * geo.C), (int64_t)L * geo.row3, geo.row3, nt, T, tid, nthr);
+    copy_tile<true>(dtile, geo.ts1, (uint8_t*)(dout + row0 * geo.C), (int64_t)L * geo.row1, geo.row1, nt, T, tid, nthr);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    for (int task = warp; task < nt * heads; task += 8) {
+    for (int task = task0; task < nt * heads; task += task_stride) {
       const int n = task / heads, h = task - n * heads;
       uint8_t* qb = tile + n * geo.row3 + h * (HD * 2);
       uint8_t* kb = qb + geo.C * 2;
@@ -250,7 +264,11 @@ __global__ void __launch_bounds__(256) tt_bwd_kernel(const bf16* __restrict__ qk
           const int i = gq + (e >> 1) * 8, j = nt2 * 8 + 2 * tq + (e & 1);
           const float v = p[nt2][e] * (dp[nt2][e] - ((e & 2) ? dl1 : dl0));   // p == 0 on padding
           ds[nt2][e] = v;
-          if (i < T && j < T) atomicAdd(dbs + (i - j + T - 1) * heads, v);   // the bias enters the logits un-scaled
+          if (FIXED_HEAD) {
+            if (g) dsacc[1][nt2][e] += v; else dsacc[0][nt2][e] += v;       // p == 0 outside the T x T block
+          } else if (i < T && j < T) {
+            atomicAdd(dbs + (i - j + T - 1) * heads, v);   // the bias enters the logits un-scaled
+          }
         }
       float dq[4][4];
       mm_pv(dq, ds, kb, geo.ts3, T, lane);                   // dQ = dS K
@@ -282,10 +300,24 @@ __global__ void __launch_bounds__(256) tt_bwd_kernel(const bf16* __restrict__ qk
       store_rows(vb, geo.ts3, dv, 1.0f, T, lane);
     }
     __syncthreads();
-    copy_tile<false>(tile, geo.ts3, (uint8_t*)(dqkv + row0 * 3 * geo.C), (int64_t)L * geo.row3, geo.row3, nt, T, tid, 256);
+    copy_tile<false>(tile, geo.ts3, (uint8_t*)(dqkv + row0 * 3 * geo.C), (int64_t)L * geo.row3, geo.row3, nt, T, tid, nthr);
+  }
+  if (FIXED_HEAD) {
+    const int h = warp % heads;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (a >= G) break;
+#pragma unroll
+      for (int nt2 = 0; nt2 < 2; ++nt2)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = gq + (e >> 1) * 8, j = nt2 * 8 + 2 * tq + (e & 1);
+          if (i < T && j < T) atomicAdd(db_s + (a * nb + (i - j + T - 1)) * heads + h, dsacc[a][nt2][e]);
+        }
+    }
   }
   __syncthreads();
-  for (int i = tid; i < G * nb * heads; i += 256) {
+  for (int i = tid; i < G * nb * heads; i += nthr) {
     const float v = db_s[i];
     if (v != 0.f) atomicAdd(dtbl + i, v);
   }
@@ -340,7 +372,17 @@ int temporal_attn_bwd_bf16(const void* qkv, const float* tbl, const void* dout, 
   make_geo(geo, T, L, heads);
   const size_t smem = (size_t)T * (geo.ts3 + geo.ts1) + (size_t)2 * G * (2 * T - 1) * heads * sizeof(float);
   if (smem > 200 * 1024) return -1;
-  cudaError_t e = cudaFuncSetAttribute(tt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // warps per block: a multiple of `heads` near 8 when there is one (-> tt_bwd_kernel<true>), else 8
+  int nw = 8;
+  auto kern = tt_bwd_kernel<false, 256, 2>;
+  if (G <= 2 && heads <= 16) {
+    nw = heads <= 8 ? (8 / heads) * heads : heads;
+    if (nw == 6) kern = tt_bwd_kernel<true, 192, 3>;
+    else if (nw == 8) kern = tt_bwd_kernel<true, 256, 2>;
+    else if (nw <= 12) kern = tt_bwd_kernel<true, 384, 1>;
+    else kern = tt_bwd_kernel<true, 512, 1>;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("temporal_attn_bwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
   const int64_t ntiles = (int64_t)G * B * ceil_div(L, geo.NT);
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -348,7 +390,7 @@ int temporal_attn_bwd_bf16(const void* qkv, const float* tbl, const void* dout, 
   if (per_sm < 1) per_sm = 1;
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
-  tt_bwd_kernel<<<grid, 256, smem, st>>>((const bf16*)qkv, tbl, (const bf16*)dout, (bf16*)dqkv, dtbl, G, B, geo);
+  kern<<<grid, nw * 32, smem, st>>>((const bf16*)qkv, tbl, (const bf16*)dout, (bf16*)dqkv, dtbl, G, B, geo);
   return check_launch("temporal_attn_bwd(tc)");
 }
 
