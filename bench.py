@@ -47,6 +47,20 @@ WORKLOAD = {"swin_t": "AVE-29 Swin-T fusion adapter train step (BASELINE.json co
             "swin_l": "AVE-29 Swin-L fusion adapter train step (run_adapt_ave29.py MM-Swin-AVE-Large)"}
 
 
+def measured_traffic(kernel, batch, model):
+    """DRAM bytes per launch of a kernel class from the newest committed ncu traffic summary for this workload
+    (scripts/traffic_summary.py); None when there is none for this model / batch."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_traffic_{model}_b{batch}.json")), reverse=True):
+        try:
+            d = json.load(open(path))["classes"].get(kernel)
+            if d:
+                return d["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -254,6 +268,10 @@ def ours(args):
         roof = {"kernel": top_name, "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
                 "frac": round(f_hbm, 4), "traffic": None, "tensor_frac": round(f_tensor, 4)}
     roof["peak_source"] = pk["source"] + ("; sustained figure: kernel timed inside a long step" if roof["bound"] == "tensor" else "")
+    roof["traffic"], tsrc = measured_traffic(top_name, B, args.model)
+    roof["algorithmic_bytes_per_launch"] = round(top["bytes"] / top["calls"])
+    if tsrc:
+        roof["traffic_source"] = tsrc
     roof["launches"] = top["calls"]
     roof["avg_launch_ms"] = round(top["ms"] / top["calls"], 4)
     roof["time_shares"] = shares

@@ -382,10 +382,16 @@ def test_xmodal_window(frames, Rr, ws, shift, rp, r, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("frames,Ln,rp,r", [(2, 196, 16, 12), (3, 49, 48, 48), (1, 100, 96, 96), (1, 784, 32, 24), (1, 3136, 16, 12)])
-def test_xmodal_global(frames, Ln, rp, r, dtype):
+@pytest.mark.parametrize("frames,Ln,rp,r,spread", [
+    (2, 196, 16, 12, False), (3, 49, 48, 48, False), (1, 100, 96, 96, False), (1, 784, 32, 24, False), (1, 3136, 16, 12, False),
+    # rows with 5x larger / 50x smaller features: logsumexp values tens of nats apart, near one-hot softmax rows
+    (2, 196, 16, 12, True), (1, 784, 32, 24, True)])
+def test_xmodal_global(frames, Ln, rp, r, spread, dtype):
     rows = frames * Ln
     h = _h_inputs(2 * rows, rp, r, dtype, 1)
+    if spread:
+        h[::7] *= 5
+        h[3::50] *= 0.02
     hpre = rnd(2 * rows, rp, dtype=dtype, seed=2)
     gate = torch.tensor([0.7, 0.3], device="cuda")
     out, att = torch.full_like(h, float("nan")), torch.full_like(h, float("nan"))
@@ -402,7 +408,8 @@ def test_xmodal_global(frames, Ln, rp, r, dtype):
     L().xmodal_global_bwd(h, hpre, gate, att, lse, dout, dh, dgate, work, frames, Ln, rp)
     r_dh, r_dg = torch.empty(2 * rows, rp, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)
     R.xmodal_global_bwd(cpu(h), cpu(hpre), cpu(gate), cpu(att), cpu(lse), cpu(dout), r_dh, r_dg, None, frames, Ln, rp)
-    assert rel(dh, r_dh) < TOL[dtype]
+    # near one-hot rows amplify the bf16 rounding of P (measured 1.3e-2): the north star's bf16 bar (2e-2) applies
+    assert rel(dh, r_dh) < (2e-2 if spread and dtype == torch.bfloat16 else TOL[dtype])
     assert rel(dgate, r_dg) < max(TOL[dtype], 1e-3)
 
 
