@@ -186,6 +186,33 @@ typedef struct StgcmaPackEntry {
 } StgcmaPackEntry;
 int stgcma_pack_params(const StgcmaPackEntry* table_dev, int n, int dtype, void* stream);
 
+/* ---- optimizer tail: Adam over every trainable tensor in ONE launch -----------
+ * Replaces torch.optim.Adam.step() of the caller (AVE/traintest_adapt_ave29.py:68,165-168: two
+ * parameter groups, betas (0.95, 0.999), weight_decay 5e-7 applied as L2 on the gradient, no
+ * amsgrad) -- ~455 tensors, i.e. hundreds of small multi-tensor launches per step in stock torch.
+ * Per element, with g = grad_scale * grad + wd * p:
+ *     m = b1 m + (1 - b1) g ;  v = b2 v + (1 - b2) g^2 ;
+ *     p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)          bc = 1 - beta^step (host computed)
+ * `table_dev` is a device array of n entries; hyper-parameters are per GROUP (<= 8), passed by value.
+ * All tensors fp32 (the caller's master weights and the flat gradient bucket).                    */
+#define STGCMA_ADAM_MAX_GROUPS 8
+typedef struct StgcmaAdamEntry {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  int32_t group;
+  int32_t pad_;
+} StgcmaAdamEntry;
+typedef struct StgcmaAdamGroups {
+  float lr[STGCMA_ADAM_MAX_GROUPS], weight_decay[STGCMA_ADAM_MAX_GROUPS], beta1[STGCMA_ADAM_MAX_GROUPS],
+      beta2[STGCMA_ADAM_MAX_GROUPS], eps[STGCMA_ADAM_MAX_GROUPS], bias_corr1[STGCMA_ADAM_MAX_GROUPS],
+      bias_corr2_sqrt[STGCMA_ADAM_MAX_GROUPS];
+} StgcmaAdamGroups;
+int stgcma_adam_step(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host, float grad_scale,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -517,9 +517,40 @@ __global__ void __launch_bounds__(256) pack_params_kernel(const StgcmaPackEntry*
   }
 }
 
+// =========================================================================================
+// Adam over a table of tensors (one launch for the whole optimizer step)
+// =========================================================================================
+__global__ void __launch_bounds__(256) adam_kernel(const StgcmaAdamEntry* __restrict__ table, const StgcmaAdamGroups hp,
+                                                   float grad_scale) {
+  const StgcmaAdamEntry e = table[blockIdx.x];
+  const int gi = e.group;
+  const float lr = hp.lr[gi], wd = hp.weight_decay[gi], b1 = hp.beta1[gi], b2 = hp.beta2[gi], eps = hp.eps[gi];
+  const float step_size = lr / hp.bias_corr1[gi], inv_bc2s = 1.f / hp.bias_corr2_sqrt[gi];
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e.numel; i += (int64_t)gridDim.y * blockDim.x) {
+    const float p = e.param[i];
+    float g = e.grad[i] * grad_scale;
+    g = fmaf(wd, p, g);                                   // L2 weight decay on the gradient (torch.optim.Adam)
+    const float m = fmaf(1.f - b1, g - e.exp_avg[i], e.exp_avg[i]);          // lerp, as torch does
+    const float v = fmaf(b2, e.exp_avg_sq[i], (1.f - b2) * g * g);
+    e.exp_avg[i] = m;
+    e.exp_avg_sq[i] = v;
+    const float denom = sqrtf(v) * inv_bc2s + eps;
+    e.param[i] = p - step_size * (m / denom);
+  }
+}
+
 }  // namespace stgcma
 
 using namespace stgcma;
+
+extern "C" int stgcma_adam_step(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host, float grad_scale,
+                                void* stream) {
+  STG_REQUIRE(n > 0 && table_dev && groups_host, "adam_step: empty table");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(n, 16);
+  adam_kernel<<<grid, 256, 0, st>>>(table_dev, *groups_host, grad_scale);
+  return check_launch("adam_step");
+}
 
 extern "C" int stgcma_pack_params(const StgcmaPackEntry* table_dev, int n, int dtype, void* stream) {
   STG_REQUIRE(n > 0 && table_dev, "pack_params: empty table");

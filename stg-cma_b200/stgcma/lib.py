@@ -39,6 +39,7 @@ _SIGNATURES = {
     "stgcma_head_pool_fwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "stgcma_head_pool_bwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "stgcma_pack_params": [_vp, _i, _i, _vp],
+    "stgcma_adam_step": [_vp, _i, _vp, ctypes.c_float, _vp],
 }
 EXPORTS = ["stgcma_last_error", "stgcma_version"] + list(_SIGNATURES)
 
@@ -277,6 +278,28 @@ PACK_ENTRY = struct.Struct("<QQiiqqii")  # mirrors StgcmaPackEntry (48 bytes)
 
 def pack_entry(src, dst, rows, cols, src_ld, dst_ld, transpose, dst_f32):
     return PACK_ENTRY.pack(src.data_ptr(), dst.data_ptr(), rows, cols, src_ld, dst_ld, int(transpose), int(dst_f32))
+
+
+ADAM_ENTRY = struct.Struct("<QQQQqii")   # mirrors StgcmaAdamEntry (48 bytes)
+ADAM_MAX_GROUPS = 8
+
+
+def adam_entry(param, grad, exp_avg, exp_avg_sq, group):
+    return ADAM_ENTRY.pack(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), group, 0)
+
+
+def adam_step(table_dev, n, groups, grad_scale=1.0, numel=0):
+    """groups: list (<= 8) of dicts lr / weight_decay / beta1 / beta2 / eps / bias_corr1 / bias_corr2_sqrt."""
+    if len(groups) > ADAM_MAX_GROUPS:
+        raise StgcmaError(f"adam_step: at most {ADAM_MAX_GROUPS} parameter groups")
+    fields = ("lr", "weight_decay", "beta1", "beta2", "eps", "bias_corr1", "bias_corr2_sqrt")
+    flat = []
+    for f in fields:
+        vals = [float(g[f]) for g in groups]
+        flat += vals + [1.0] * (ADAM_MAX_GROUPS - len(vals))
+    hp = (ctypes.c_float * len(flat))(*flat)      # StgcmaAdamGroups, passed by host pointer
+    _call("stgcma_adam_step", _p(table_dev), n, ctypes.cast(hp, ctypes.c_void_p), ctypes.c_float(grad_scale),
+          cost=(0.0, 28.0 * numel))
 
 
 def pack_params(table_dev, n, dtype_code):

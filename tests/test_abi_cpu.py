@@ -34,6 +34,21 @@ def test_pack_entry_matches_struct_layout():
     assert lib.PACK_ENTRY.size == 48  # sizeof(StgcmaPackEntry): 2 pointers, 2 int32, 2 int64, 2 int32
 
 
+def test_adam_entry_matches_struct_layout():
+    import stgcma.lib as lib
+    assert lib.ADAM_ENTRY.size == 48  # sizeof(StgcmaAdamEntry): 4 pointers, int64, 2 int32
+
+
+def test_fused_adam_refuses_cpu_parameters():
+    from stgcma.optim import FusedAdam
+    import stgcma.lib as lib
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = FusedAdam([p], lr=1e-3)
+    p.grad = torch.ones(4)
+    with pytest.raises(lib.StgcmaError):
+        opt.step()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import stgcma.lib as lib
     monkeypatch.setattr(lib, "_lib", None)

@@ -455,3 +455,35 @@ def test_bad_arguments_fail_loudly():
         lib.gemm(x, x, x, 8, 100, 100)  # K % 8 != 0 for bf16
     with pytest.raises(lib.StgcmaError):
         lib.xmodal_global_fwd(x, torch.zeros(2, device="cuda"), x, x, torch.zeros(8, device="cuda"), 1, 4, 20)  # rp unsupported
+
+
+# ---------------------------------------------------------------------------------------------
+def test_fused_adam_matches_torch_adam():
+    """stgcma_adam_step against torch.optim.Adam with the caller's hyper-parameters (traintest_adapt_ave29.py:68):
+    two groups with different learning rates, L2 weight decay, 6 steps, an LR change and a parameter without grad."""
+    from stgcma.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(12, 96), (12,), (96, 12), (96,), (1,), (19, 3), (512, 1536), (29, 512), (7,)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    kw = dict(weight_decay=5e-7, betas=(0.95, 0.999))
+    mk = lambda ps: [{"params": ps[:6], "lr": 5e-3}, {"params": ps[6:], "lr": 5e-4}]
+    ref, ours = torch.optim.Adam(mk(ref_p), **kw), FusedAdam(mk(our_p), **kw)
+    for it in range(6):
+        if it == 3:
+            for o in (ref, ours):
+                o.param_groups[0]["lr"] = 1e-3
+        for i, (a, b) in enumerate(zip(ref_p, our_p)):
+            if i == 8 and it == 3:      # a tensor without a gradient is skipped and keeps its own step count, like torch
+                a.grad = b.grad = None
+                continue
+            gr = torch.randn(*shapes[i], generator=g).cuda() * (10.0 if i == 4 else 1.0)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        ref.step()
+        ours.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ref_p, our_p):
+        assert rel(b.detach(), a.detach()) < 1e-6
+    sd = ours.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert rel(ours.state[our_p[0]]["exp_avg_sq"], ref.state[ref_p[0]]["exp_avg_sq"]) < 1e-6

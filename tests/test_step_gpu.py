@@ -193,16 +193,19 @@ def test_full_width_properties(dtype):
     assert rel(f0, mm) < 1e-6 or torch.equal(f0, mm)
 
 
-def test_caller_loop_autocast_gradscaler():
+@pytest.mark.parametrize("fused_adam", [False, True])
+def test_caller_loop_autocast_gradscaler(fused_adam):
     """The reference caller wraps the model in fp16 autocast + GradScaler + nn.DataParallel
-    (traintest_adapt_ave29.py:32-33,119,161-168): the drop-in must survive that unchanged."""
+    (traintest_adapt_ave29.py:32-33,119,161-168): the drop-in must survive that unchanged -- with the caller's
+    torch.optim.Adam and with stgcma.optim.FusedAdam (same update as one launch) in its place."""
     cfg = O.SwinAVEConfig(**TINY)
     sd = O.make_state(cfg, seed=3)
     a, v, labels = O.make_inputs(cfg, 2, seed=3)
     m = build(TINY, "fusion", torch.bfloat16, sd)
     dp = torch.nn.DataParallel(m, device_ids=[0])
     params = [p for p in dp.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=5e-7, betas=(0.95, 0.999))
+    from stgcma.optim import FusedAdam
+    opt = (FusedAdam if fused_adam else torch.optim.Adam)(params, lr=1e-4, weight_decay=5e-7, betas=(0.95, 0.999))
     scaler = torch.amp.GradScaler("cuda")
     before = [p.detach().clone() for p in params]
     losses = []
