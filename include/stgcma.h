@@ -208,7 +208,8 @@ typedef struct StgcmaAdamEntry {
 typedef struct StgcmaAdamGroups {
   float lr[STGCMA_ADAM_MAX_GROUPS], weight_decay[STGCMA_ADAM_MAX_GROUPS], beta1[STGCMA_ADAM_MAX_GROUPS],
       beta2[STGCMA_ADAM_MAX_GROUPS], eps[STGCMA_ADAM_MAX_GROUPS], bias_corr1[STGCMA_ADAM_MAX_GROUPS],
-      bias_corr2_sqrt[STGCMA_ADAM_MAX_GROUPS];
+      bias_corr2_sqrt[STGCMA_ADAM_MAX_GROUPS],
+      one_minus_beta1[STGCMA_ADAM_MAX_GROUPS], one_minus_beta2[STGCMA_ADAM_MAX_GROUPS];  /* rounded from double, as torch does */
 } StgcmaAdamGroups;
 int stgcma_adam_step(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host, float grad_scale,
                      void* stream);

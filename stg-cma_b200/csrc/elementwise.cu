@@ -525,16 +525,18 @@ __global__ void __launch_bounds__(256) adam_kernel(const StgcmaAdamEntry* __rest
   const StgcmaAdamEntry e = table[blockIdx.x];
   const int gi = e.group;
   const float lr = hp.lr[gi], wd = hp.weight_decay[gi], b1 = hp.beta1[gi], b2 = hp.beta2[gi], eps = hp.eps[gi];
-  const float step_size = lr / hp.bias_corr1[gi], inv_bc2s = 1.f / hp.bias_corr2_sqrt[gi];
+  const float step_size = lr / hp.bias_corr1[gi], bc2s = hp.bias_corr2_sqrt[gi];
+  const float omb1 = hp.one_minus_beta1[gi], omb2 = hp.one_minus_beta2[gi];
+  (void)b1;
   for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e.numel; i += (int64_t)gridDim.y * blockDim.x) {
     const float p = e.param[i];
     float g = e.grad[i] * grad_scale;
     g = fmaf(wd, p, g);                                   // L2 weight decay on the gradient (torch.optim.Adam)
-    const float m = fmaf(1.f - b1, g - e.exp_avg[i], e.exp_avg[i]);          // lerp, as torch does
-    const float v = fmaf(b2, e.exp_avg_sq[i], (1.f - b2) * g * g);
+    const float m = fmaf(omb1, g - e.exp_avg[i], e.exp_avg[i]);              // lerp, as torch does
+    const float v = fmaf(omb2 * g, g, b2 * e.exp_avg_sq[i]);
     e.exp_avg[i] = m;
     e.exp_avg_sq[i] = v;
-    const float denom = sqrtf(v) * inv_bc2s + eps;
+    const float denom = sqrtf(v) / bc2s + eps;
     e.param[i] = p - step_size * (m / denom);
   }
 }

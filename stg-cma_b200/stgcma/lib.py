@@ -292,10 +292,10 @@ def adam_step(table_dev, n, groups, grad_scale=1.0, numel=0):
     """groups: list (<= 8) of dicts lr / weight_decay / beta1 / beta2 / eps / bias_corr1 / bias_corr2_sqrt."""
     if len(groups) > ADAM_MAX_GROUPS:
         raise StgcmaError(f"adam_step: at most {ADAM_MAX_GROUPS} parameter groups")
-    fields = ("lr", "weight_decay", "beta1", "beta2", "eps", "bias_corr1", "bias_corr2_sqrt")
+    fields = ("lr", "weight_decay", "beta1", "beta2", "eps", "bias_corr1", "bias_corr2_sqrt", "one_minus_beta1", "one_minus_beta2")
     flat = []
     for f in fields:
-        vals = [float(g[f]) for g in groups]
+        vals = [float(g[f]) if f in g else 1.0 - float(g["beta" + f[-1]]) for g in groups]
         flat += vals + [1.0] * (ADAM_MAX_GROUPS - len(vals))
     hp = (ctypes.c_float * len(flat))(*flat)      # StgcmaAdamGroups, passed by host pointer
     _call("stgcma_adam_step", _p(table_dev), n, ctypes.cast(hp, ctypes.c_void_p), ctypes.c_float(grad_scale),
