@@ -239,11 +239,14 @@ def ours(args):
     # every rank runs the step (its backward holds the gradient all-reduce); only rank 0 brackets the launches
     prof = None
     torch.cuda.synchronize()
+    eng = m.engine()
+    side_dw, eng.side_stream_dw = eng.side_stream_dw, False   # serialise the dW side stream: clean per-kernel durations
     if rank == 0:
         lib.profile_start()
     step_resident()
     if rank == 0:
         prof = lib.profile_stop()
+    eng.side_stream_dw = side_dw
     barrier()
 
     total_clips = B * world * args.steps

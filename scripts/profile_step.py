@@ -35,6 +35,7 @@ def main():
         loss.backward()
         opt.step()
 
+    m.engine().side_stream_dw = False   # one stream: the launch list is the step's critical path
     for _ in range(args.warm):
         step()
     torch.cuda.synchronize()

@@ -9,6 +9,7 @@
 //       fp32: plain CUDA-core tiled GEMM (the check mode; also the numerics reference).
 //   stgcma_gemm_tn   dW += A^T . B   (trainable adapter / head weights), split over rows,
 //                    fp32 atomics into the gradient bucket.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace stgcma {
@@ -119,6 +120,8 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int64_t off, int p
     float t[8];
     unpack8(r.a[ps][0], t);
 #pragma unroll
+    // (the MUFU-free polynomials of gelu_poly.cuh are ~25 % cheaper here but moved one stage-2 temporal-bias-table
+    //  gradient of the T = 2 golden fixture from 1.9e-2 to 2.4e-2 relative L2: the erf forms stay)
     for (int i = 0; i < 8; ++i) v[i] *= (MODE == STGCMA_EPI_DGELU) ? gelu_grad_fast(t[i]) : t[i];
   }
   if (OUT_F32) store8(reinterpret_cast<float*>(p.out) + off, v);
@@ -457,7 +460,12 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   p.K = K;
   p.groups = groups;
   // tile width: the multiple of 16 (<= bn_max) that wastes the fewest padded columns, larger on ties
-  const int occ = (K >= 1024) ? 1 : 2;
+  // One CTA per SM with tiles up to 128 x 256 and a 4-stage ring when the tensor pipe is the limit: K >= 1024, or
+  // K >= 256 with a wide N unless the epilogue evaluates GELU / GELU' at K < 768 (then two CTAs' epilogue warps per SM
+  // matter more than the deeper ring).  Measured per shape with scripts/gemm_shapes.py (profiles/r01f): qkv stage 2
+  // 775 -> 859 TFLOP/s, qkv stage 3 908 -> 1176, proj stage 3 780 -> 961; mlp.fc1 + GELU stage 2 532 -> 509 (kept at 2).
+  const bool act_epi = ep.mode == STGCMA_EPI_GELU || ep.mode == STGCMA_EPI_DGELU;
+  const int occ = (K >= 1024 || (K >= 256 && N >= 384 && (!act_epi || K >= 768))) ? 1 : 2;
   const int bn_max = occ == 1 ? 256 : 128;
   int best_bn = 16;
   int64_t best_cost = -1;

@@ -20,6 +20,7 @@ Design points (B200-first, not a translation of the reference's module tree):
 All compute is in the C-ABI library; torch is used for memory, streams and the collective only.
 """
 import math
+import os
 
 import torch
 
@@ -64,6 +65,10 @@ class SwinAVEEngine:
         self.train_key = None
         self.generation = 0
         self.dp_allreduce = True    # all-reduce the gradient bucket when torch.distributed is initialised
+        # dW of the adapters (gemm_tn) is off the dX critical path: it runs on a side stream, overlapping the next
+        # kernels of the main chain, and is joined before its operand buffers are rewritten (backward())
+        self.side_stream_dw = os.environ.get("STGCMA_SIDE_DW", "1") != "0"
+        self._side = None
 
     # ------------------------------------------------------------------------------------------
     # parameters
@@ -457,15 +462,40 @@ class SwinAVEEngine:
         dx, dxb = buf(f"dB{s}", M, C, dtype=sdt), buf(f"dBb{s}", M, C)
         L_.layernorm_bwd(dxn, sv["x_final"], slot("h_mean"), slot("h_rstd"), fz["norm"]["g"], None, dx, M, C, dx_copy=dxb)
 
+        side = None
+        main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None   # (the CPU schedule tests mock the kernels)
+        if self.side_stream_dw and main is not None:
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+        pending = []   # events of side-stream dW work whose operand buffers the main chain has not rewritten yet
+
+        def join_side():
+            while pending:
+                main.wait_event(pending.pop())
+
         def adapter_grads(prefix_names, d_out, h_in, d_hpre, x_in, M, C, r, rp, rowscale):
             """dW2/db2 from (d_out, h_in); dW1/db1 from (d_hpre, x_in), per modality."""
             Mg = M // 2
-            for gi, nm in enumerate(prefix_names):
-                rs = None if rowscale is None else rowscale[gi * Mg:(gi + 1) * Mg]
-                L_.gemm_tn(d_out[gi * Mg:], h_in[gi * Mg:], g(nm + ".D_fc2.weight"), Mg, C, r, lda=C, ldb=rp, ldo=r,
-                           rowscale=rs, csumA=g(nm + ".D_fc2.bias"))
-                L_.gemm_tn(d_hpre[gi * Mg:], x_in[gi * Mg:], g(nm + ".D_fc1.weight"), Mg, r, C, lda=rp, ldb=C, ldo=C,
-                           csumA=g(nm + ".D_fc1.bias"))
+
+            def run():
+                for gi, nm in enumerate(prefix_names):
+                    rs = None if rowscale is None else rowscale[gi * Mg:(gi + 1) * Mg]
+                    L_.gemm_tn(d_out[gi * Mg:], h_in[gi * Mg:], g(nm + ".D_fc2.weight"), Mg, C, r, lda=C, ldb=rp, ldo=r,
+                               rowscale=rs, csumA=g(nm + ".D_fc2.bias"))
+                    L_.gemm_tn(d_hpre[gi * Mg:], x_in[gi * Mg:], g(nm + ".D_fc1.weight"), Mg, r, C, lda=rp, ldb=C, ldo=C,
+                               csumA=g(nm + ".D_fc1.bias"))
+            if side is None:
+                run()
+                return
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                run()
+                done = torch.cuda.Event()
+                done.record(side)
+            pending.append(done)
 
         for s in reversed(range(cfg.num_stages)):
             C, R, heads = cfg.stage_dim(s), cfg.stage_res(s), cfg.num_heads[s]
@@ -493,6 +523,7 @@ class SwinAVEEngine:
                 assert goffs[pfx + "gate_a"][0] == goffs[pfx + "gate_v"][0] + 1
                 dgate2 = gbuf[goffs[pfx + "gate_v"][0]:goffs[pfx + "gate_v"][0] + 2]
                 # ---------------- (G) backward: dx = dX3 ----------------
+                join_side()   # the previous sub-block's dW kernels read dhpre / dxb, rewritten below
                 A = p["S"]
                 y = slot(k + "y")
                 dh2 = buf(f"dh{s}", M, rp)
@@ -521,6 +552,7 @@ class SwinAVEEngine:
                 dx2, dx2b = buf(f"dD{s}", M, C, dtype=sdt), buf(f"dDb{s}", M, C)
                 L_.layernorm_bwd(dxn, sv[k + "x2"], slot(k + "g_mean"), slot(k + "g_rstd"), f["n2g"], dx, dx2, M, C, dx_copy=dx2b)
                 # ---------------- (S) backward: dx2 ----------------
+                join_side()
                 A = p["S2"]
                 at = slot(k + "attn")
                 if fusion:
@@ -546,6 +578,7 @@ class SwinAVEEngine:
                 L_.layernorm_bwd(dxn, sv[k + "x1"], slot(k + "s_mean"), slot(k + "s_rstd"), f["n1g"], dx2, dx1, M, C, dx_copy=dx1b)
                 # ---------------- (T) backward: dx1 ----------------
                 if blk.t_attn:
+                    join_side()
                     A = p["T"]
                     dp = sv["dp"][(s, i)]
                     L_.gemm(dx1b, A["w2t"], dhpre, M, rp, C, groups=2, rowscale=dp, aux=slot(k + "t_hpre"), epi=L_.EPI_DGELU)
@@ -570,6 +603,7 @@ class SwinAVEEngine:
                 else:
                     dx, dxb = dx1, dx1b
 
+        join_side()
         out = gbuf.clone()
         if self.dp_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
