@@ -240,13 +240,15 @@ def ours(args):
     prof = None
     torch.cuda.synchronize()
     eng = m.engine()
-    side_dw, eng.side_stream_dw = eng.side_stream_dw, False   # serialise the dW side stream: clean per-kernel durations
+    # one chain on one stream for this step (no micro-batch lanes, no dW side stream): clean per-kernel durations
+    side_dw, eng.side_stream_dw = eng.side_stream_dw, False
+    lanes, eng.lanes = eng.lanes, 1
     if rank == 0:
         lib.profile_start()
     step_resident()
     if rank == 0:
         prof = lib.profile_stop()
-    eng.side_stream_dw = side_dw
+    eng.side_stream_dw, eng.lanes = side_dw, lanes
     barrier()
 
     total_clips = B * world * args.steps
@@ -291,6 +293,7 @@ def ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD[args.model], "clips_per_gpu": B, "global_batch": B * world, "frames": 10,
                    "parallelism": f"dp{world} (clips sharded, adapter-grad bucket all-reduce)" if world > 1 else "single GPU",
+                   "streams": f"{m.engine().lanes} micro-batch lane(s) per GPU on separate CUDA streams + dW side stream",
                    "optimizer": "Adam (the caller's groups / betas / weight decay) as one fused launch, inside the timed step",
                    "l2": "no flush needed: one step streams several GB of activations (>> 126 MB L2)",
                    "step_flop_fraction_of_bf16_peak": round(step_frac, 4)},

@@ -35,7 +35,8 @@ def main():
         loss.backward()
         opt.step()
 
-    m.engine().side_stream_dw = False   # one stream: the launch list is the step's critical path
+    m.engine().side_stream_dw = False   # one chain on one stream: the launch list is the whole step, serialised
+    m.engine().lanes = 1
     for _ in range(args.warm):
         step()
     torch.cuda.synchronize()

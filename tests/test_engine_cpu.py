@@ -100,7 +100,7 @@ def test_drop_path_and_head_dropout(monkeypatch):
         p.requires_grad_(O.is_trainable(n))
     torch.manual_seed(0)
     out = m(a, v, "fusion")
-    saved = out.grad_fn.saved if hasattr(out.grad_fn, "saved") else None
+    saved = m.engine().saved_masks(out.grad_fn.saved) if hasattr(out.grad_fn, "saved") else None
     assert saved is not None
     B, T = 2, cfg.num_frames
     masks = {}

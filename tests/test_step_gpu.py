@@ -140,7 +140,7 @@ def test_drop_path_and_dropout_replay():
     m.mlp_head[1].train()
     torch.manual_seed(0)
     out = m(a.cuda(), v.cuda(), "fusion")
-    saved = out.grad_fn.saved
+    saved = m.engine().saved_masks(out.grad_fn.saved)
     B, T = 2, cfg.num_frames
     masks = {}
     for s in range(cfg.num_stages):
