@@ -235,3 +235,20 @@ def test_caller_loop_autocast_gradscaler(fused_adam):
     assert any(not torch.equal(b, p.detach()) for b, p in zip(before, params))
     key = next(iter(dp.state_dict()))
     assert key.startswith("module.")
+
+
+def test_micro_batch_lanes_match_single_chain():
+    """STGCMA_LANES option (engine.lanes): the clips split over two CUDA streams give the single chain's logits bit for
+    bit (every op is per-clip independent) and its gradients up to the order of the fp32 atomics."""
+    cfg = O.SwinAVEConfig(**TINY)
+    sd = O.make_state(cfg, seed=11)
+    a, v, labels = O.make_inputs(cfg, 3, seed=11)
+    m = build(TINY, "fusion", torch.bfloat16, sd)
+    m.engine().lanes = 1
+    out1, _, g1 = step(m, a, v, labels, "fusion")
+    m.zero_grad(set_to_none=True)
+    m.engine().lanes = 2          # 3 clips -> lanes of 1 and 2 clips
+    out2, _, g2 = step(m, a, v, labels, "fusion")
+    assert torch.equal(out1, out2)
+    for n in g1:
+        assert rel(g2[n], g1[n]) < 2e-3, n
