@@ -88,6 +88,9 @@ int stgcma_layernorm_bwd(const void* dy, const void* x, const float* mean, const
  * M/groups rows, part g using W[g] (groups = 2: per-modality adapter weights).
  * bf16 mode: tcgen05/TMEM kernel fed by TMA; needs K, lda, ldw multiples of 8 and 16-byte
  * aligned A / W; N multiple of 8.  res1/res2/aux/out/out_pre share row stride ldo.
+ * Skinny contractions with a residual (K <= 128, K % 16 == 0, N % 16 == 0, res1 != NULL, LINEAR:
+ * the adapters' D_fc2 + residual adds and the dX of D_fc1) are HBM streams and run in a warp-level
+ * streaming kernel instead (gemm_skinny.cu); same arguments, same results.
  * out_dtype: type of `out` and `res1` -- `dtype`, or STGCMA_F32 when they are the fp32 residual
  * stream (x_new = x + branch); res2 / aux / out_pre always have the activation type.          */
 int stgcma_gemm(const void* A, const void* W, const float* bias, const void* res1, const void* res2,
@@ -118,7 +121,9 @@ int stgcma_mlp_bwd(const void* dhpre, const void* dxb, const float* x, const flo
 /* ---- weight gradients of the trainable nn.Linear layers (adapters, head) -------------------
  * dW[i, j] += sum_m rowscale[m] * A[m, i] * B[m, j]   (i < Ka, j < Nb; dW fp32, row stride ldo)
  * csumA[i] += sum_m rowscale[m] * A[m, i]  (when non-NULL);  csumB likewise.  Accumulates
- * (atomics) so the destination is normally a slice of the pre-zeroed flat gradient bucket.   */
+ * (atomics) so the destination is normally a slice of the pre-zeroed flat gradient bucket.
+ * bf16 mode (tensor cores): rowscale[m] * A[m, :] is rounded to bf16 before the product, which is
+ * exact for the DropPath keep masks {0, 1/keep} up to the rounding of 1/keep (2^-9 relative).   */
 int stgcma_gemm_tn(const void* A, const void* B, const float* rowscale, float* dW, float* csumA,
                    float* csumB, int64_t M, int Ka, int Nb, int64_t lda, int64_t ldb, int64_t ldo, int dtype,
                    void* stream);
