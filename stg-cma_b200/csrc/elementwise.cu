@@ -221,6 +221,11 @@ __global__ void __launch_bounds__(256) ln_bwd_rr_kernel(const TD* __restrict__ d
   const float mean = ok ? mean_in[row] : 0.f, rstd = ok ? rstd_in[row] : 0.f;
   const TD* dyrow = dy + (ok ? row : 0) * (int64_t)C;
   float gg[VMAX][4], xh[VMAX][4];
+  // Short rows (VMAX = 4): the residual gradient is loaded together with dy / x, before the row reduction, so that a
+  // row has ONE exposed memory round trip instead of two (every load of the row is in flight at once).  dres may alias
+  // dx: this lane still reads its own elements before it writes them.
+  constexpr bool EARLY = VMAX <= 4;
+  float rr[EARLY ? VMAX : 1][4];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(256) ln_bwd_rr_kernel(const TD* __restrict__ d
       float d4[4], x4[4], g4[4];
       load4(dyrow + c, d4);
       load4(x + addr.at(c), x4);
+      if (EARLY && dres) load4(dres + addr.at(c), rr[EARLY ? i : 0]);
       load4(gamma + c, g4);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -252,16 +258,12 @@ __global__ void __launch_bounds__(256) ln_bwd_rr_kernel(const TD* __restrict__ d
       const int64_t off = addr.at(4 * (sub + LPR * i));
       float o[4];
       if (dres) {
-        // dres may alias dx: this lane reads its 4 elements before it writes them
         float r4[4];
-        const TX* rp = dres + off;
-        if (sizeof(TX) == 4) {
-          const float4 t = *reinterpret_cast<const float4*>(rp);
-          r4[0] = t.x; r4[1] = t.y; r4[2] = t.z; r4[3] = t.w;
+        if (EARLY) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r4[e] = rr[EARLY ? i : 0][e];
         } else {
-          const uint2 t = *reinterpret_cast<const uint2*>(rp);
-          r4[0] = __uint_as_float(t.x << 16); r4[1] = __uint_as_float(t.x & 0xffff0000u);
-          r4[2] = __uint_as_float(t.y << 16); r4[3] = __uint_as_float(t.y & 0xffff0000u);
+          load4(dres + off, r4);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = r4[e] + rstd * (gg[i][e] - s1 - xh[i][e] * s2);
