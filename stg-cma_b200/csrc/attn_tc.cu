@@ -44,15 +44,21 @@ __device__ __forceinline__ void win_setup(Win& w, int wy, int wx, int ws, int sh
   }
 }
 
-// gather [N rows][HG*32] slices (column offset col0 of a row of `ld_g` elements) into a [NP][LD] tile; pad rows zero
+// gather [N rows][HG*32] slices (column offset col0 of a row of `ld_g` elements) into a [NP][LD] tile; pad rows zero.
+// Thread layout: CH = HG*4 consecutive threads copy the CH 16-byte chunks of one row, NTH / CH rows per pass -- the
+// (row, chunk) split is computed once per thread instead of a division per chunk (this loop was ~13 % of the kernel's
+// instructions; ncu source page, profiles/r01f).
 template <int HG>
 __device__ __forceinline__ void gather_async(uint8_t* tile, const bf16* __restrict__ src, int64_t frame_row0, int64_t ld_g,
                                              int col0, const Win& w, int N, int tid) {
-  constexpr int CH = HG * 4, LD = HG * 64 + 16;
-  for (int e = tid; e < NP * CH; e += NTH) {
-    const int r = e / CH, c = e - r * CH;
-    uint8_t* dst = tile + r * LD + c * 16;
-    if (r < N) cp_async16(dst, src + (frame_row0 + w.tok[r]) * ld_g + col0 + c * 8);
+  constexpr int CH = HG * 4, LD = HG * 64 + 16, RPP = NTH / CH;   // rows per pass
+  const int r0 = tid / CH, c = tid - r0 * CH;
+  if (r0 >= RPP) return;                                            // NTH % CH leftover threads
+  const bf16* base = src + frame_row0 * ld_g + col0 + c * 8;
+  uint8_t* dst = tile + r0 * LD + c * 16;
+#pragma unroll 1
+  for (int r = r0; r < NP; r += RPP, dst += RPP * LD) {
+    if (r < N) cp_async16(dst, base + (int64_t)w.tok[r] * ld_g);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
 }
@@ -113,16 +119,18 @@ __device__ __forceinline__ void stage_rows(uint8_t* tile, int LD, const float (&
 }
 
 // coalesced scatter of a staged [N rows][HG*32] tile to the token-major destination (16 B per lane, a row's HG*64 B
-// segment is contiguous in global memory)
+// segment is contiguous in global memory); same thread layout as gather_async
 template <int HG>
 __device__ __forceinline__ void scatter_rows(const uint8_t* tile, bf16* __restrict__ dst, int64_t frame_row0, int64_t ld_g,
                                              int col0, const Win& w, int N, int tid) {
-  constexpr int CH = HG * 4, LD = HG * 64 + 16;
-  for (int e = tid; e < N * CH; e += NTH) {
-    const int r = e / CH, c = e - r * CH;
-    const uint4 v = *reinterpret_cast<const uint4*>(tile + r * LD + c * 16);
-    *reinterpret_cast<uint4*>(dst + (frame_row0 + w.tok[r]) * ld_g + col0 + c * 8) = v;
-  }
+  constexpr int CH = HG * 4, LD = HG * 64 + 16, RPP = NTH / CH;
+  const int r0 = tid / CH, c = tid - r0 * CH;
+  if (r0 >= RPP) return;
+  bf16* base = dst + frame_row0 * ld_g + col0 + c * 8;
+  const uint8_t* sp = tile + r0 * LD + c * 16;
+#pragma unroll 1
+  for (int r = r0; r < N; r += RPP, sp += RPP * LD)
+    *reinterpret_cast<uint4*>(base + (int64_t)w.tok[r] * ld_g) = *reinterpret_cast<const uint4*>(sp);
 }
 
 // 16 x 56 raw scores: A = 16 rows of `ta` (row block rb), B = rows of `tb` as [n][k]; features h*32 .. +31

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
   constexpr int LD = Cfg<RP>::LD, KS = Cfg<RP>::KS, BM = NW * 16;
   extern __shared__ __align__(16) uint8_t xsm[];
   uint8_t* own = xsm;                 // [BM][LD]
-  uint8_t* oth = own + BM * LD;       // 2 x [BN][LD]
+  uint8_t* oth = own + BM * LD;       // 3 x [BN][LD]  (ring: one block-wide barrier per streamed tile instead of two)
   const int z = blockIdx.z;
   const int64_t frame = blockIdx.y;
   const int r0 = blockIdx.x * BM;
@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
   load_rows_async<RP>(own, hown, r0, BM, L, tid, NW * 32);
   load_rows_async<RP>(oth, hoth, 0, BN, L, tid, NW * 32);
   cp_async_commit();
+  if (nkt > 1) load_rows_async<RP>(oth + BN * LD, hoth, BN, BN, L, tid, NW * 32);
+  cp_async_commit();
 
   uint32_t qa[KS][4];
   float acc[2 * KS][4];
@@ -74,15 +76,11 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};  // log2 domain; l = per-thread partial sums
 
   for (int kt = 0; kt < nkt; ++kt) {
-    uint8_t* cur = oth + (kt & 1) * BN * LD;
-    if (kt + 1 < nkt) {
-      load_rows_async<RP>(oth + ((kt + 1) & 1) * BN * LD, hoth, (kt + 1) * BN, BN, L, tid, NW * 32);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    uint8_t* cur = oth + (kt % 3) * BN * LD;
+    cp_async_wait<1>();   // tile kt has landed (tile kt + 1 may still be in flight)
+    __syncthreads();      // ... for every thread, and every warp is done with tile kt - 1, whose buffer is refilled now
+    if (kt + 2 < nkt) load_rows_async<RP>(oth + ((kt + 2) % 3) * BN * LD, hoth, (kt + 2) * BN, BN, L, tid, NW * 32);
+    cp_async_commit();
     if (kt == 0) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) load_a(qa[ks], own, LD, warp * 16, ks * 16, lane);
@@ -154,7 +152,6 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
         mma16816(acc[2 * n2 + 1], pa, b[2], b[3]);
       }
     }
-    __syncthreads();  // everyone is done with `cur` before the next iteration's prefetch overwrites it
   }
 
   const float gz = gate[z];
@@ -199,10 +196,10 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
   extern __shared__ __align__(16) uint8_t xsm[];
   uint8_t* own_h = xsm;                       // [BM][LD]
   uint8_t* own_d = own_h + BM * LD;           // [BM][LD]  dout of the own rows
-  uint8_t* oth_h = own_d + BM * LD;           // 2 x [BN][LD]
-  uint8_t* oth_d = oth_h + 2 * BN * LD;       // 2 x [BN][LD]
-  float* col_lse = reinterpret_cast<float*>(oth_d + 2 * BN * LD);  // 2 x [BN]  lse (log2 domain) of the streamed rows
-  float* col_D = col_lse + 2 * BN;                                  // 2 x [BN]
+  uint8_t* oth_h = own_d + BM * LD;           // 3 x [BN][LD]  (ring of 3: one block-wide barrier per streamed tile)
+  uint8_t* oth_d = oth_h + 3 * BN * LD;       // 3 x [BN][LD]
+  float* col_lse = reinterpret_cast<float*>(oth_d + 3 * BN * LD);  // 3 x [BN]  lse (log2 domain) of the streamed rows
+  float* col_D = col_lse + 3 * BN;                                  // 3 x [BN]
   const int z = blockIdx.z;
   const int64_t frame = blockIdx.y;
   const int r0 = blockIdx.x * BM;
@@ -218,7 +215,7 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
   const int nkt = (L + BN - 1) / BN;
 
   auto load_cols = [&](int kt) {
-    const int buf = kt & 1;
+    const int buf = kt % 3;
     load_rows_async<RP>(oth_h + buf * BN * LD, h + off_oth, kt * BN, BN, L, tid, NW * 32);
     load_rows_async<RP>(oth_d + buf * BN * LD, dout + off_oth, kt * BN, BN, L, tid, NW * 32);
     if (tid < BN) {
@@ -234,6 +231,8 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
   load_rows_async<RP>(own_d, dout + off_own, r0, BM, L, tid, NW * 32);
   load_cols(0);
   cp_async_commit();
+  if (nkt > 1) load_cols(1);
+  cp_async_commit();
 
   const int ra = r0 + warp * 16 + g, rb = ra + 8;
   // invalid own rows: lse = +inf -> P1 = 0 ; their P2 contributions are discarded with the row
@@ -246,17 +245,13 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
   for (int i = 0; i < 2 * KS; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
   for (int kt = 0; kt < nkt; ++kt) {
-    const int buf = kt & 1;
+    const int buf = kt % 3;
     const uint8_t* ch = oth_h + buf * BN * LD;
     const uint8_t* cd = oth_d + buf * BN * LD;
-    if (kt + 1 < nkt) {
-      load_cols(kt + 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    cp_async_wait<1>();   // tile kt has landed
+    __syncthreads();      // ... for everyone; tile kt - 1 is no longer read: its buffers are refilled with tile kt + 2
+    if (kt + 2 < nkt) load_cols(kt + 2);
+    cp_async_commit();
     if (kt == 0) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
@@ -328,7 +323,6 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
         }
       }
     }
-    __syncthreads();
   }
 
 #pragma unroll
@@ -356,7 +350,7 @@ template <int RP, int NW>
 static int fwd_launch(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L,
                       cudaStream_t st) {
   constexpr int LD = Cfg<RP>::LD, BM = NW * 16;
-  const size_t smem = (size_t)(BM + 2 * BN) * LD;
+  const size_t smem = (size_t)(BM + 3 * BN) * LD;
   auto kern = xg_fwd_kernel<RP, NW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("xmodal_global_fwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
@@ -369,7 +363,7 @@ template <int RP, int NW>
 static int bwd_launch(const void* h, const void* hpre, const float* gate, const float* lse, const float* D,
                       const void* dout, void* dh, int64_t frames, int L, cudaStream_t st) {
   constexpr int LD = Cfg<RP>::LD, BM = NW * 16;
-  const size_t smem = (size_t)(2 * BM + 4 * BN) * LD + 4 * BN * sizeof(float);
+  const size_t smem = (size_t)(2 * BM + 6 * BN) * LD + 6 * BN * sizeof(float);
   auto kern = xg_bwd_kernel<RP, NW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("xmodal_global_bwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
