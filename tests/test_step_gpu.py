@@ -97,6 +97,34 @@ def test_tiny_step_vs_oracle(mode, dtype):
     check_grads(g, r_g, TOL[dtype], metric=rel if dtype == torch.float32 else rel_l2)
 
 
+# Reduced-depth versions of the other presets of run_adapt_ave29.py:156-181: different head groupings (window attention
+# HG = 2 / 3), adapter widths r = 16 / 32 / 96 (cross-modal kernels RP = 16 / 32 / 96, skinny GEMM K = 16 / 32 / 96 and its
+# 64-column blocks when C % 48 != 0), C = 128 / 256 (fused MLP with two N pieces / 128-wide hidden chunks) and 192 / 384
+SMALL_PRESETS = {
+    "swin_b_like": dict(img_size=112, num_frames=2, embed_dim=128, depths=[2, 2], num_heads=[4, 8],
+                        adapter_mlp_ratio=[0.125, 0.125], label_dim=11),
+    "swin_l_like": dict(img_size=112, num_frames=2, embed_dim=192, depths=[2, 2], num_heads=[6, 12],
+                        adapter_mlp_ratio=[0.5, 0.25], label_dim=11),
+}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("preset", sorted(SMALL_PRESETS))
+def test_other_presets_step_vs_oracle(preset, dtype):
+    kw = SMALL_PRESETS[preset]
+    cfg = O.SwinAVEConfig(**kw)
+    sd = O.make_state(cfg, seed=5, bf16_exact=True)
+    a, v, labels = O.make_inputs(cfg, 2, seed=5)
+    sd64 = {k: (t.double() if t.is_floating_point() else t) for k, t in sd.items()}
+    r_out, r_loss, r_g = O.train_step(sd64, a.double(), v.double(), labels.double(), cfg, "fusion")
+    m = build(kw, "fusion", dtype, sd)
+    out, loss, g = step(m, a, v, labels, "fusion")
+    assert rel(out, r_out) < TOL[dtype]
+    assert abs(loss - float(r_loss)) < TOL[dtype] * max(1.0, abs(float(r_loss)))
+    assert set(r_g) <= set(g)
+    check_grads(g, r_g, TOL[dtype], metric=rel if dtype == torch.float32 else rel_l2)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion", "swin_t_T10_B2_fusion"])
 def test_step_vs_reference_golden(name, dtype):
