@@ -159,6 +159,28 @@ def test_mlp_bwd(case):
     assert rel(dxn, r) < 1e-2
 
 
+@pytest.mark.parametrize("f32", [False, True])
+def test_gemm_skinny_padded_strides(f32):
+    """The skinny residual kernel with lda > K and ldo > N (adapter hidden tensors and arena slices are stored padded),
+    M not a multiple of 16 and a K of 5 k-steps; the pad columns of `out` must stay untouched."""
+    M, N, K, lda, ldo, groups = 2 * 75, 96, 80, 96, 128, 2
+    dtype = torch.bfloat16
+    odt = torch.float32 if f32 else dtype
+    A = rnd(M, lda, dtype=dtype, seed=1)
+    W = rnd(groups, N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    bias = rnd(groups, N, dtype=torch.float32, seed=3)
+    res1 = rnd(M, ldo, dtype=odt, seed=4)
+    res2 = rnd(M, ldo, dtype=dtype, seed=5)
+    out = torch.full((M, ldo), 7.0, dtype=odt, device="cuda")
+    L().gemm(A, W, out, M, N, K, bias=bias, res1=res1, res2=res2, lda=lda, ldo=ldo, groups=groups)
+    torch.cuda.synchronize()
+    Mg = M // groups
+    ref = torch.cat([cpu(A)[g * Mg:(g + 1) * Mg, :K].double() @ cpu(W)[g].double().t() + cpu(bias)[g].double() for g in range(groups)])
+    ref = ref + cpu(res1)[:, :N].double() + cpu(res2)[:, :N].double()
+    assert rel(out[:, :N], ref) < (1e-4 if f32 else 1e-2)
+    assert float((out[:, N:] - 7.0).abs().max()) == 0.0
+
+
 def test_gemm_bf16_padded_strides():
     """lda / ldo larger than the logical width (adapter hidden tensors are stored padded)."""
     M, N, K, lda, ldo = 200, 96, 16, 32, 128
