@@ -47,7 +47,9 @@ enum {
   STGCMA_EPI_LINEAR = 0,  /* out = res1 + res2 + v                 (each term optional)      */
   STGCMA_EPI_GELU = 1,    /* out = gelu_erf(v); out_pre = v when out_pre != NULL            */
   STGCMA_EPI_DGELU = 2,   /* out = v * gelu_erf'(aux[m,n])   (backward through nn.GELU)      */
-  STGCMA_EPI_MULAUX = 3   /* out = v * aux[m,n]              (dropout keep-mask)             */
+  STGCMA_EPI_MULAUX = 3,  /* out = v * aux[m,n]              (dropout keep-mask)             */
+  STGCMA_EPI_QGELU = 4,   /* out = v * sigmoid(1.702 v) (CLIP's QuickGELU, CLIP_AVE.py:41-43); out_pre = v   */
+  STGCMA_EPI_DQGELU = 5   /* out = v * d/dx[x sigmoid(1.702 x)](aux[m,n])                          */
 };
 
 const char* stgcma_last_error(void);

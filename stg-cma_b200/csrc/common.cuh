@@ -128,6 +128,12 @@ __device__ __forceinline__ float gelu_fast(float x) {
   erf_exp_fast(x, e, g);
   return 0.5f * x * (1.0f + e);
 }
+// QuickGELU of the CLIP MLP (CLIP_AVE.py:41-43): x * sigmoid(1.702 x), and its derivative s (1 + 1.702 x (1 - s))
+__device__ __forceinline__ float qgelu(float x) { return x * __fdividef(1.0f, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float qgelu_grad(float x) {
+  const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * x));
+  return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
+}
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float e, g;
   erf_exp_fast(x, e, g);

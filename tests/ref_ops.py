@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from oracle import swin_ave_oracle as O
 
-EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX = 0, 1, 2, 3
+EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX, EPI_QGELU, EPI_DQGELU = 0, 1, 2, 3, 4, 5
 
 
 def _view2d(t, rows, cols, ld):
@@ -120,6 +120,14 @@ def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, 
         o.copy_(_gelu(v))
     elif epi == EPI_DGELU:
         o.copy_(v * _dgelu(_c(_view2d(aux, M, N, ldo))))
+    elif epi == EPI_QGELU:        # CLIP's QuickGELU, CLIP_AVE.py:41-43
+        if out_pre is not None:
+            _view2d(out_pre, M, N, ldo).copy_(v)
+        o.copy_(v * torch.sigmoid(1.702 * v))
+    elif epi == EPI_DQGELU:
+        a = _c(_view2d(aux, M, N, ldo))
+        sg = torch.sigmoid(1.702 * a)
+        o.copy_(v * sg * (1.0 + 1.702 * a * (1.0 - sg)))
     else:
         o.copy_(v * _c(_view2d(aux, M, N, ldo)))
 

@@ -51,6 +51,10 @@ GEMM_CASES = [
     (20, 32, 512, 1, R.EPI_LINEAR, dict(bias=True)),
     (640, 768, 3072, 1, R.EPI_LINEAR, dict(bias=True, res1=True)),    # mlp.fc2 at stage 3: 48 k-blocks
     (50000, 288, 96, 1, R.EPI_LINEAR, dict(bias=True)),               # many tiles per CTA (persistent loop, phases)
+    # QuickGELU epilogues (first brick of the CLIP-ViT row): mlp.c_fc 768 -> 3072 and its dX
+    (394, 3072, 768, 1, R.EPI_QGELU, dict(bias=True, out_pre=True)),
+    (394, 768, 3072, 1, R.EPI_DQGELU, dict(aux=True)),
+    (200, 256, 64, 1, R.EPI_QGELU, dict(bias=True)),
     # skinny-K residual GEMMs (gemm_skinny.cu): adapter D_fc2 + residual adds into the fp32 stream, and the dX of D_fc1
     (2 * 147, 96, 16, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, f32=True)),     # ragged 16-row slabs per group
     (2 * 1000, 384, 32, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, f32=True)),
