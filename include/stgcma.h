@@ -167,11 +167,15 @@ int stgcma_xmodal_window_fwd(const void* h, const float* gate, void* out, void* 
 int stgcma_xmodal_window_bwd(const void* h, const void* hpre, const float* gate, const void* attn_out,
                              const void* dout, void* dh, float* dgate, int64_t frames, int R, int ws,
                              int shift, int rp, int dtype, void* stream);
+/* global variant with different row counts per modality (CLIP: 197 video / 49 audio tokens per frame,
+ * CLIP_AVE.py:380-397): modality 0 has L rows per frame, modality 1 has La (La <= 0 means La = L); the
+ * tensors are then the two blocks stacked: [frames, L, rp] followed by [frames, La, rp]; lse / work
+ * likewise [frames * L] followed by [frames * La].                                                  */
 int stgcma_xmodal_global_fwd(const void* h, const float* gate, void* out, void* attn_out, float* lse,
-                             int64_t frames, int L, int rp, int dtype, void* stream);
+                             int64_t frames, int L, int La, int rp, int dtype, void* stream);
 int stgcma_xmodal_global_bwd(const void* h, const void* hpre, const float* gate, const void* attn_out,
                              const float* lse, const void* dout, void* dh, float* dgate, float* work,
-                             int64_t frames, int L, int rp, int dtype, void* stream);
+                             int64_t frames, int L, int La, int rp, int dtype, void* stream);
 
 /* ---- head pooling: mean over the N tokens of a frame, cat(audio, video) (Swin_AVE.py:1588-1596)
  * xn [2, frames, N, C] (video, audio) -> feat [frames, 2C] = [audio mean | video mean].      */

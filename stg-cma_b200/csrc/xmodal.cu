@@ -228,7 +228,7 @@ constexpr int XG_TILE = 64;
 template <typename T, int RP>
 __global__ void __launch_bounds__(128) xmodal_global_fwd_kernel(const T* __restrict__ h, const float* __restrict__ gate,
                                                                 T* __restrict__ out, T* __restrict__ attn_out,
-                                                                float* __restrict__ lse, int64_t frames, int L) {
+                                                                float* __restrict__ lse, int64_t frames, int L, int La) {
   extern __shared__ float xs[];
   constexpr int LDH = RP + 1, LDP = XG_TILE + 1;
   float* own = xs;
@@ -237,24 +237,28 @@ __global__ void __launch_bounds__(128) xmodal_global_fwd_kernel(const T* __restr
   const int z = blockIdx.z;
   const int64_t frame = blockIdx.y;
   const int r0 = blockIdx.x * XG_TILE;
-  const int64_t mod_stride = frames * (int64_t)L * RP;
-  const T* hown = h + (z ? mod_stride : 0) + frame * (int64_t)L * RP;
-  const T* hoth = h + (z ? 0 : mod_stride) + frame * (int64_t)L * RP;
+  // rows per frame: L (first modality, video) and La (second, audio); the rows of the two modalities are stacked
+  const int Lown = z ? La : L, Loth = z ? L : La;
+  if (r0 >= Lown) return;
+  const int64_t row_own0 = (z ? frames * (int64_t)L : 0) + frame * (int64_t)Lown;
+  const int64_t row_oth0 = (z ? 0 : frames * (int64_t)L) + frame * (int64_t)Loth;
+  const T* hown = h + row_own0 * RP;
+  const T* hoth = h + row_oth0 * RP;
   const int tid = threadIdx.x;
   for (int e = tid; e < XG_TILE * RP; e += 128) {
     const int i = e / RP, d = e - i * RP;
-    own[i * LDH + d] = (r0 + i < L) ? ld_f(hown + (int64_t)(r0 + i) * RP + d) : 0.f;
+    own[i * LDH + d] = (r0 + i < Lown) ? ld_f(hown + (int64_t)(r0 + i) * RP + d) : 0.f;
   }
   const int row = tid >> 1, half = tid & 1;
   float acc[RP / 2];
 #pragma unroll
   for (int d = 0; d < RP / 2; ++d) acc[d] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
-  for (int c0 = 0; c0 < L; c0 += XG_TILE) {
+  for (int c0 = 0; c0 < Loth; c0 += XG_TILE) {
     __syncthreads();
     for (int e = tid; e < XG_TILE * RP; e += 128) {
       const int j = e / RP, d = e - j * RP;
-      oth[j * LDH + d] = (c0 + j < L) ? ld_f(hoth + (int64_t)(c0 + j) * RP + d) : 0.f;
+      oth[j * LDH + d] = (c0 + j < Loth) ? ld_f(hoth + (int64_t)(c0 + j) * RP + d) : 0.f;
     }
     __syncthreads();
     float s[XG_TILE / 2];
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(128) xmodal_global_fwd_kernel(const T* __restr
       float a = 0.f;
 #pragma unroll
       for (int d = 0; d < RP; ++d) a = fmaf(own[row * LDH + d], oth[j * LDH + d], a);
-      a = (c0 + j < L) ? a : -INFINITY;
+      a = (c0 + j < Loth) ? a : -INFINITY;
       s[jj] = a;
       mx = fmaxf(mx, a);
     }
@@ -291,10 +295,10 @@ __global__ void __launch_bounds__(128) xmodal_global_fwd_kernel(const T* __restr
       for (int d = 0; d < RP / 2; ++d) acc[d] = fmaf(p, oth[j * LDH + half + 2 * d], acc[d]);
     }
   }
-  if (r0 + row < L) {
+  if (r0 + row < Lown) {
     const float inv = 1.f / l_run;
     const float g = gate[z];
-    const int64_t base = (z ? mod_stride : 0) + (frame * (int64_t)L + r0 + row) * RP;
+    const int64_t base = (row_own0 + r0 + row) * RP;
 #pragma unroll
     for (int d = 0; d < RP / 2; ++d) {
       const int dd = half + 2 * d;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(128) xmodal_global_fwd_kernel(const T* __restr
       st_f(attn_out + base + dd, a);
       st_f(out + base + dd, own[row * LDH + dd] + g * a);
     }
-    if (half == 0) lse[((int64_t)z * frames + frame) * L + r0 + row] = m_run + __logf(l_run);
+    if (half == 0) lse[row_own0 + r0 + row] = m_run + __logf(l_run);
   }
 }
 
@@ -310,18 +314,19 @@ __global__ void __launch_bounds__(128) xmodal_global_fwd_kernel(const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) xmodal_prep_kernel(const T* __restrict__ dout, const T* __restrict__ attn_out,
                                                           const float* __restrict__ gate, float* __restrict__ D,
-                                                          float* __restrict__ dgate, int64_t rows_per_mod, int rp) {
+                                                          float* __restrict__ dgate, int64_t rows0, int64_t rows1, int rp) {
   __shared__ float red[8];
   const int m = blockIdx.y;
+  const int64_t rows_per_mod = m ? rows1 : rows0, row_base = m ? rows0 : 0;   // modality 1 follows the rows0 rows of modality 0
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float g = gate[m];
   float tot = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows_per_mod; row += (int64_t)gridDim.x * 8) {
-    const int64_t base = ((int64_t)m * rows_per_mod + row) * rp;
+    const int64_t base = (row_base + row) * rp;
     float a = 0.f;
     for (int d = lane; d < rp; d += 32) a = fmaf(ld_f(dout + base + d), ld_f(attn_out + base + d), a);
     a = warp_sum(a);
-    if (lane == 0) D[(int64_t)m * rows_per_mod + row] = g * a;
+    if (lane == 0) D[row_base + row] = g * a;
     tot += a;
   }
   if (lane == 0) red[warp] = tot;
@@ -338,7 +343,7 @@ template <typename T, int RP>
 __global__ void __launch_bounds__(128) xmodal_global_bwd_kernel(const T* __restrict__ h, const T* __restrict__ hpre,
                                                                 const float* __restrict__ gate, const float* __restrict__ lse,
                                                                 const float* __restrict__ D, const T* __restrict__ dout,
-                                                                T* __restrict__ dh, int64_t frames, int L) {
+                                                                T* __restrict__ dh, int64_t frames, int L, int La) {
   extern __shared__ float xs[];
   constexpr int LDH = RP + 1, LDP = XG_TILE + 1;
   float* own = xs;                        // h of the own rows
@@ -352,38 +357,40 @@ __global__ void __launch_bounds__(128) xmodal_global_bwd_kernel(const T* __restr
   const int z = blockIdx.z;
   const int64_t frame = blockIdx.y;
   const int r0 = blockIdx.x * XG_TILE;
-  const int64_t mod_stride = frames * (int64_t)L * RP;
-  const int64_t off_own = (z ? mod_stride : 0) + frame * (int64_t)L * RP;
-  const int64_t off_oth = (z ? 0 : mod_stride) + frame * (int64_t)L * RP;
+  const int Lown = z ? La : L, Loth = z ? L : La;
+  if (r0 >= Lown) return;
+  const int64_t row_own0 = (z ? frames * (int64_t)L : 0) + frame * (int64_t)Lown;
+  const int64_t row_oth0 = (z ? 0 : frames * (int64_t)L) + frame * (int64_t)Loth;
+  const int64_t off_own = row_own0 * RP, off_oth = row_oth0 * RP;
   const float g_own = gate[z], g_oth = gate[1 - z];
-  const float* lse_own_p = lse + ((int64_t)z * frames + frame) * L;
-  const float* lse_oth_p = lse + ((int64_t)(1 - z) * frames + frame) * L;
-  const float* D_own_p = D + ((int64_t)z * frames + frame) * L;
-  const float* D_oth_p = D + ((int64_t)(1 - z) * frames + frame) * L;
+  const float* lse_own_p = lse + row_own0;
+  const float* lse_oth_p = lse + row_oth0;
+  const float* D_own_p = D + row_own0;
+  const float* D_oth_p = D + row_oth0;
   const int tid = threadIdx.x;
   for (int e = tid; e < XG_TILE * RP; e += 128) {
     const int i = e / RP, d = e - i * RP;
-    const bool ok = r0 + i < L;
+    const bool ok = r0 + i < Lown;
     own[i * LDH + d] = ok ? ld_f(h + off_own + (int64_t)(r0 + i) * RP + d) : 0.f;
     gown[i * LDH + d] = ok ? g_own * ld_f(dout + off_own + (int64_t)(r0 + i) * RP + d) : 0.f;
   }
   const int row = tid >> 1, half = tid & 1;
-  const bool row_ok = r0 + row < L;
+  const bool row_ok = r0 + row < Lown;
   const float my_lse = row_ok ? lse_own_p[r0 + row] : 0.f;
   const float my_D = row_ok ? D_own_p[r0 + row] : 0.f;
   float acc[RP / 2];
 #pragma unroll
   for (int d = 0; d < RP / 2; ++d) acc[d] = 0.f;
-  for (int c0 = 0; c0 < L; c0 += XG_TILE) {
+  for (int c0 = 0; c0 < Loth; c0 += XG_TILE) {
     __syncthreads();
     for (int e = tid; e < XG_TILE * RP; e += 128) {
       const int j = e / RP, d = e - j * RP;
-      const bool ok = c0 + j < L;
+      const bool ok = c0 + j < Loth;
       oth[j * LDH + d] = ok ? ld_f(h + off_oth + (int64_t)(c0 + j) * RP + d) : 0.f;
       goth[j * LDH + d] = ok ? g_oth * ld_f(dout + off_oth + (int64_t)(c0 + j) * RP + d) : 0.f;
     }
     if (tid < XG_TILE) {
-      const bool ok = c0 + tid < L;
+      const bool ok = c0 + tid < Loth;
       lse_o[tid] = ok ? lse_oth_p[c0 + tid] : 0.f;
       D_o[tid] = ok ? D_oth_p[c0 + tid] : 0.f;
     }
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(128) xmodal_global_bwd_kernel(const T* __restr
         dp2 = fmaf(goth[j * LDH + d], ho, dp2);
       }
       float w = 0.f, p2 = 0.f;
-      if (row_ok && c0 + j < L) {
+      if (row_ok && c0 + j < Loth) {
         const float p1 = __expf(s - my_lse);       // own row as query
         p2 = __expf(s - lse_o[j]);                 // other row j as query, own row as key/value
         w = p1 * (dp1 - my_D) + p2 * (dp2 - D_o[j]);
@@ -433,25 +440,25 @@ __global__ void __launch_bounds__(128) xmodal_global_bwd_kernel(const T* __restr
 
 template <typename T, int RP>
 static int xg_fwd_launch(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L,
-                         cudaStream_t st) {
+                         int La, cudaStream_t st) {
   const size_t smem = sizeof(float) * (2 * XG_TILE * (RP + 1) + XG_TILE * (XG_TILE + 1));
   auto kern = xmodal_global_fwd_kernel<T, RP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("xmodal_global_fwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
-  dim3 grid((unsigned)ceil_div(L, XG_TILE), (unsigned)frames, 2);
-  kern<<<grid, 128, smem, st>>>((const T*)h, gate, (T*)out, (T*)attn_out, lse, frames, L);
+  dim3 grid((unsigned)ceil_div(L > La ? L : La, XG_TILE), (unsigned)frames, 2);
+  kern<<<grid, 128, smem, st>>>((const T*)h, gate, (T*)out, (T*)attn_out, lse, frames, L, La);
   return check_launch("xmodal_global_fwd");
 }
 
 template <typename T, int RP>
 static int xg_bwd_launch(const void* h, const void* hpre, const float* gate, const float* lse, const float* D, const void* dout,
-                         void* dh, int64_t frames, int L, cudaStream_t st) {
+                         void* dh, int64_t frames, int L, int La, cudaStream_t st) {
   const size_t smem = sizeof(float) * (4 * XG_TILE * (RP + 1) + 2 * XG_TILE * (XG_TILE + 1) + 2 * XG_TILE);
   auto kern = xmodal_global_bwd_kernel<T, RP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("xmodal_global_bwd: smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
-  dim3 grid((unsigned)ceil_div(L, XG_TILE), (unsigned)frames, 2);
-  kern<<<grid, 128, smem, st>>>((const T*)h, (const T*)hpre, gate, lse, D, (const T*)dout, (T*)dh, frames, L);
+  dim3 grid((unsigned)ceil_div(L > La ? L : La, XG_TILE), (unsigned)frames, 2);
+  kern<<<grid, 128, smem, st>>>((const T*)h, (const T*)hpre, gate, lse, D, (const T*)dout, (T*)dh, frames, L, La);
   return check_launch("xmodal_global_bwd");
 }
 
@@ -466,10 +473,10 @@ static int xg_bwd_launch(const void* h, const void* hpre, const float* gate, con
   }
 
 // bf16 production kernels (tensor cores), xmodal_tc.cu
-int xmodal_global_fwd_bf16(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L,
+int xmodal_global_fwd_bf16(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L, int La,
                            int rp, cudaStream_t st);
 int xmodal_global_bwd_bf16(const void* h, const void* hpre, const float* gate, const float* lse, const float* D,
-                           const void* dout, void* dh, int64_t frames, int L, int rp, cudaStream_t st);
+                           const void* dout, void* dh, int64_t frames, int L, int La, int rp, cudaStream_t st);
 // xmodal_win_tc.cu
 int xmodal_window_fwd_bf16(const void* h, const float* gate, void* out, void* attn_out, int64_t frames, int R, int ws,
                            int shift, int rp, cudaStream_t st);
@@ -544,15 +551,16 @@ extern "C" int stgcma_xmodal_window_bwd(const void* h, const void* hpre, const f
 }
 
 extern "C" int stgcma_xmodal_global_fwd(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames,
-                                        int L, int rp, int dtype, void* stream) {
+                                        int L, int La, int rp, int dtype, void* stream) {
+  if (La <= 0) La = L;
   STG_REQUIRE(frames > 0 && frames <= 65535 && L > 0, "xmodal_global_fwd: bad sizes frames=%lld L=%d", (long long)frames, L);
   STG_REQUIRE(lse, "xmodal_global_fwd: lse required");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = STGCMA_OK;
   if (dtype == STGCMA_F32) {
-    XG_DISPATCH_RP(rp, rc = (xg_fwd_launch<float, RP_>(h, gate, out, attn_out, lse, frames, L, st)));
+    XG_DISPATCH_RP(rp, rc = (xg_fwd_launch<float, RP_>(h, gate, out, attn_out, lse, frames, L, La, st)));
   } else if (dtype == STGCMA_BF16) {
-    rc = xmodal_global_fwd_bf16(h, gate, out, attn_out, lse, frames, L, rp, st);
+    rc = xmodal_global_fwd_bf16(h, gate, out, attn_out, lse, frames, L, La, rp, st);
   } else {
     STG_REQUIRE(false, "xmodal_global_fwd: bad dtype %d", dtype);
   }
@@ -562,25 +570,26 @@ extern "C" int stgcma_xmodal_global_fwd(const void* h, const float* gate, void* 
 
 extern "C" int stgcma_xmodal_global_bwd(const void* h, const void* hpre, const float* gate, const void* attn_out,
                                         const float* lse, const void* dout, void* dh, float* dgate, float* work, int64_t frames,
-                                        int L, int rp, int dtype, void* stream) {
+                                        int L, int La, int rp, int dtype, void* stream) {
+  if (La <= 0) La = L;
   STG_REQUIRE(frames > 0 && frames <= 65535 && L > 0, "xmodal_global_bwd: bad sizes frames=%lld L=%d", (long long)frames, L);
   STG_REQUIRE(lse && dgate && work, "xmodal_global_bwd: lse, dgate and work ([2, frames, L] fp32) required");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t rows = frames * L;
-  int pg = (int)ceil_div(rows, 8);
+  const int64_t rows0 = frames * L, rows1 = frames * (int64_t)La;
+  int pg = (int)ceil_div(rows0 > rows1 ? rows0 : rows1, 8);
   if (pg > sm_count() * 8) pg = sm_count() * 8;
   dim3 pgrid(pg, 2);
   int rc = STGCMA_OK;
   if (dtype == STGCMA_F32) {
-    xmodal_prep_kernel<float><<<pgrid, 256, 0, st>>>((const float*)dout, (const float*)attn_out, gate, work, dgate, rows, rp);
+    xmodal_prep_kernel<float><<<pgrid, 256, 0, st>>>((const float*)dout, (const float*)attn_out, gate, work, dgate, rows0, rows1, rp);
     rc = check_launch("xmodal_prep");
     if (rc) return rc;
-    XG_DISPATCH_RP(rp, rc = (xg_bwd_launch<float, RP_>(h, hpre, gate, lse, work, dout, dh, frames, L, st)));
+    XG_DISPATCH_RP(rp, rc = (xg_bwd_launch<float, RP_>(h, hpre, gate, lse, work, dout, dh, frames, L, La, st)));
   } else if (dtype == STGCMA_BF16) {
-    xmodal_prep_kernel<bf16><<<pgrid, 256, 0, st>>>((const bf16*)dout, (const bf16*)attn_out, gate, work, dgate, rows, rp);
+    xmodal_prep_kernel<bf16><<<pgrid, 256, 0, st>>>((const bf16*)dout, (const bf16*)attn_out, gate, work, dgate, rows0, rows1, rp);
     rc = check_launch("xmodal_prep");
     if (rc) return rc;
-    rc = xmodal_global_bwd_bf16(h, hpre, gate, lse, work, dout, dh, frames, L, rp, st);
+    rc = xmodal_global_bwd_bf16(h, hpre, gate, lse, work, dout, dh, frames, L, La, rp, st);
   } else {
     STG_REQUIRE(false, "xmodal_global_bwd: bad dtype %d", dtype);
   }

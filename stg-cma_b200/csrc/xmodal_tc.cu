@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_rows_async(uint8_t* tile, const bf16* __res
 template <int RP, int NW>
 __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict__ h, const float* __restrict__ gate,
                                                          bf16* __restrict__ out, bf16* __restrict__ attn_out,
-                                                         float* __restrict__ lse, int64_t frames, int L) {
+                                                         float* __restrict__ lse, int64_t frames, int L, int La) {
   constexpr int LD = Cfg<RP>::LD, KS = Cfg<RP>::KS, BM = NW * 16;
   extern __shared__ __align__(16) uint8_t xsm[];
   uint8_t* own = xsm;                 // [BM][LD]
@@ -57,16 +57,20 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
   const int z = blockIdx.z;
   const int64_t frame = blockIdx.y;
   const int r0 = blockIdx.x * BM;
-  const int64_t mod_stride = frames * (int64_t)L * RP;
-  const bf16* hown = h + (z ? mod_stride : 0) + frame * (int64_t)L * RP;
-  const bf16* hoth = h + (z ? 0 : mod_stride) + frame * (int64_t)L * RP;
+  // rows per frame: L for the first modality (video), La for the second (audio; = L in the Swin model, 197 / 49 in CLIP)
+  const int Lown = z ? La : L, Loth = z ? L : La;
+  if (r0 >= Lown) return;
+  const int64_t row_own0 = (z ? frames * (int64_t)L : 0) + frame * (int64_t)Lown;
+  const int64_t row_oth0 = (z ? 0 : frames * (int64_t)L) + frame * (int64_t)Loth;
+  const bf16* hown = h + row_own0 * RP;
+  const bf16* hoth = h + row_oth0 * RP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nkt = (L + BN - 1) / BN;
+  const int nkt = (Loth + BN - 1) / BN;
 
-  load_rows_async<RP>(own, hown, r0, BM, L, tid, NW * 32);
-  load_rows_async<RP>(oth, hoth, 0, BN, L, tid, NW * 32);
+  load_rows_async<RP>(own, hown, r0, BM, Lown, tid, NW * 32);
+  load_rows_async<RP>(oth, hoth, 0, BN, Loth, tid, NW * 32);
   cp_async_commit();
-  if (nkt > 1) load_rows_async<RP>(oth + BN * LD, hoth, BN, BN, L, tid, NW * 32);
+  if (nkt > 1) load_rows_async<RP>(oth + BN * LD, hoth, BN, BN, Loth, tid, NW * 32);
   cp_async_commit();
 
   uint32_t qa[KS][4];
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
     uint8_t* cur = oth + (kt % 3) * BN * LD;
     cp_async_wait<1>();   // tile kt has landed (tile kt + 1 may still be in flight)
     __syncthreads();      // ... for every thread, and every warp is done with tile kt - 1, whose buffer is refilled now
-    if (kt + 2 < nkt) load_rows_async<RP>(oth + ((kt + 2) % 3) * BN * LD, hoth, (kt + 2) * BN, BN, L, tid, NW * 32);
+    if (kt + 2 < nkt) load_rows_async<RP>(oth + ((kt + 2) % 3) * BN * LD, hoth, (kt + 2) * BN, BN, Loth, tid, NW * 32);
     cp_async_commit();
     if (kt == 0) {
 #pragma unroll
@@ -99,14 +103,14 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
       }
     }
     const int jbase = kt * BN;
-    const bool tail = jbase + BN > L;
+    const bool tail = jbase + BN > Loth;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float v = s[i][e] * kLog2e;
-        if (tail && jbase + i * 8 + 2 * t + (e & 1) >= L) v = -INFINITY;
+        if (tail && jbase + i * 8 + 2 * t + (e & 1) >= Loth) v = -INFINITY;
         s[i][e] = v;
       }
       mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
@@ -158,18 +162,18 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
   const float l0 = quad_sum(l_run[0]), l1 = quad_sum(l_run[1]);
   const float inv0 = 1.f / l0, inv1 = 1.f / l1;
   const int ra = r0 + warp * 16 + g, rb = ra + 8;
-  const int64_t base = (z ? mod_stride : 0) + frame * (int64_t)L * RP;
+  const int64_t base = row_own0 * RP;
 #pragma unroll
   for (int i = 0; i < 2 * KS; ++i) {
     const int col = i * 8 + 2 * t;
-    if (ra < L) {
+    if (ra < Lown) {
       const float a0 = acc[i][0] * inv0, a1 = acc[i][1] * inv0;
       const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(own + (warp * 16 + g) * LD + col * 2);
       *reinterpret_cast<uint32_t*>(attn_out + base + (int64_t)ra * RP + col) = pack_bf16(a0, a1);
       *reinterpret_cast<uint32_t*>(out + base + (int64_t)ra * RP + col) =
           pack_bf16(__bfloat162float(o.x) + gz * a0, __bfloat162float(o.y) + gz * a1);
     }
-    if (rb < L) {
+    if (rb < Lown) {
       const float a0 = acc[i][2] * inv1, a1 = acc[i][3] * inv1;
       const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(own + (warp * 16 + g + 8) * LD + col * 2);
       *reinterpret_cast<uint32_t*>(attn_out + base + (int64_t)rb * RP + col) = pack_bf16(a0, a1);
@@ -178,9 +182,9 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
     }
   }
   if (t == 0) {
-    float* lp = lse + ((int64_t)z * frames + frame) * L;
-    if (ra < L) lp[ra] = (m_run[0] + log2f(l0)) * 0.6931471805599453f;
-    if (rb < L) lp[rb] = (m_run[1] + log2f(l1)) * 0.6931471805599453f;
+    float* lp = lse + row_own0;
+    if (ra < Lown) lp[ra] = (m_run[0] + log2f(l0)) * 0.6931471805599453f;
+    if (rb < Lown) lp[rb] = (m_run[1] + log2f(l1)) * 0.6931471805599453f;
   }
 }
 
@@ -191,7 +195,7 @@ template <int RP, int NW>
 __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ hpre,
                                                          const float* __restrict__ gate, const float* __restrict__ lse,
                                                          const float* __restrict__ D, const bf16* __restrict__ dout,
-                                                         bf16* __restrict__ dh, int64_t frames, int L) {
+                                                         bf16* __restrict__ dh, int64_t frames, int L, int La) {
   constexpr int LD = Cfg<RP>::LD, KS = Cfg<RP>::KS, BM = NW * 16;
   extern __shared__ __align__(16) uint8_t xsm[];
   uint8_t* own_h = xsm;                       // [BM][LD]
@@ -203,32 +207,34 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
   const int z = blockIdx.z;
   const int64_t frame = blockIdx.y;
   const int r0 = blockIdx.x * BM;
-  const int64_t mod_stride = frames * (int64_t)L * RP;
-  const int64_t off_own = (z ? mod_stride : 0) + frame * (int64_t)L * RP;
-  const int64_t off_oth = (z ? 0 : mod_stride) + frame * (int64_t)L * RP;
+  const int Lown = z ? La : L, Loth = z ? L : La;
+  if (r0 >= Lown) return;
+  const int64_t row_own0 = (z ? frames * (int64_t)L : 0) + frame * (int64_t)Lown;
+  const int64_t row_oth0 = (z ? 0 : frames * (int64_t)L) + frame * (int64_t)Loth;
+  const int64_t off_own = row_own0 * RP, off_oth = row_oth0 * RP;
   const float g_own = gate[z], g_oth = gate[1 - z];
-  const float* lse_own_p = lse + ((int64_t)z * frames + frame) * L;
-  const float* lse_oth_p = lse + ((int64_t)(1 - z) * frames + frame) * L;
-  const float* D_own_p = D + ((int64_t)z * frames + frame) * L;
-  const float* D_oth_p = D + ((int64_t)(1 - z) * frames + frame) * L;
+  const float* lse_own_p = lse + row_own0;
+  const float* lse_oth_p = lse + row_oth0;
+  const float* D_own_p = D + row_own0;
+  const float* D_oth_p = D + row_oth0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nkt = (L + BN - 1) / BN;
+  const int nkt = (Loth + BN - 1) / BN;
 
   auto load_cols = [&](int kt) {
     const int buf = kt % 3;
-    load_rows_async<RP>(oth_h + buf * BN * LD, h + off_oth, kt * BN, BN, L, tid, NW * 32);
-    load_rows_async<RP>(oth_d + buf * BN * LD, dout + off_oth, kt * BN, BN, L, tid, NW * 32);
+    load_rows_async<RP>(oth_h + buf * BN * LD, h + off_oth, kt * BN, BN, Loth, tid, NW * 32);
+    load_rows_async<RP>(oth_d + buf * BN * LD, dout + off_oth, kt * BN, BN, Loth, tid, NW * 32);
     if (tid < BN) {
       const int j = kt * BN + tid;
-      const bool ok = j < L;
+      const bool ok = j < Loth;
       // invalid columns get lse = +inf -> P2 = exp2(s - inf) = 0
       col_lse[buf * BN + tid] = ok ? lse_oth_p[j] * kLog2e : INFINITY;
       col_D[buf * BN + tid] = ok ? D_oth_p[j] : 0.f;
     }
   };
 
-  load_rows_async<RP>(own_h, h + off_own, r0, BM, L, tid, NW * 32);
-  load_rows_async<RP>(own_d, dout + off_own, r0, BM, L, tid, NW * 32);
+  load_rows_async<RP>(own_h, h + off_own, r0, BM, Lown, tid, NW * 32);
+  load_rows_async<RP>(own_d, dout + off_own, r0, BM, Lown, tid, NW * 32);
   load_cols(0);
   cp_async_commit();
   if (nkt > 1) load_cols(1);
@@ -236,8 +242,8 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
 
   const int ra = r0 + warp * 16 + g, rb = ra + 8;
   // invalid own rows: lse = +inf -> P1 = 0 ; their P2 contributions are discarded with the row
-  const float lse0 = ra < L ? lse_own_p[ra] * kLog2e : INFINITY, lse1 = rb < L ? lse_own_p[rb] * kLog2e : INFINITY;
-  const float D0 = ra < L ? D_own_p[ra] : 0.f, D1 = rb < L ? D_own_p[rb] : 0.f;
+  const float lse0 = ra < Lown ? lse_own_p[ra] * kLog2e : INFINITY, lse1 = rb < Lown ? lse_own_p[rb] * kLog2e : INFINITY;
+  const float D0 = ra < Lown ? D_own_p[ra] : 0.f, D1 = rb < Lown ? D_own_p[rb] : 0.f;
 
   uint32_t ha[KS][4], da[KS][4];
   float acc[2 * KS][4];
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int r = hrow ? rb : ra;
-      if (r >= L) continue;
+      if (r >= Lown) continue;
       const int lr = warp * 16 + g + hrow * 8;
       const __nv_bfloat162 dd = *reinterpret_cast<const __nv_bfloat162*>(own_d + lr * LD + col * 2);
       float v0 = __bfloat162float(dd.x) + acc[i][2 * hrow], v1 = __bfloat162float(dd.y) + acc[i][2 * hrow + 1];
@@ -348,27 +354,27 @@ __global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict_
 
 template <int RP, int NW>
 static int fwd_launch(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L,
-                      cudaStream_t st) {
+                      int La, cudaStream_t st) {
   constexpr int LD = Cfg<RP>::LD, BM = NW * 16;
   const size_t smem = (size_t)(BM + 3 * BN) * LD;
   auto kern = xg_fwd_kernel<RP, NW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("xmodal_global_fwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
-  dim3 grid((unsigned)ceil_div(L, BM), (unsigned)frames, 2);
-  kern<<<grid, NW * 32, smem, st>>>((const bf16*)h, gate, (bf16*)out, (bf16*)attn_out, lse, frames, L);
+  dim3 grid((unsigned)ceil_div(L > La ? L : La, BM), (unsigned)frames, 2);
+  kern<<<grid, NW * 32, smem, st>>>((const bf16*)h, gate, (bf16*)out, (bf16*)attn_out, lse, frames, L, La);
   return check_launch("xmodal_global_fwd(tc)");
 }
 
 template <int RP, int NW>
 static int bwd_launch(const void* h, const void* hpre, const float* gate, const float* lse, const float* D,
-                      const void* dout, void* dh, int64_t frames, int L, cudaStream_t st) {
+                      const void* dout, void* dh, int64_t frames, int L, int La, cudaStream_t st) {
   constexpr int LD = Cfg<RP>::LD, BM = NW * 16;
   const size_t smem = (size_t)(2 * BM + 6 * BN) * LD + 6 * BN * sizeof(float);
   auto kern = xg_bwd_kernel<RP, NW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("xmodal_global_bwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
-  dim3 grid((unsigned)ceil_div(L, BM), (unsigned)frames, 2);
-  kern<<<grid, NW * 32, smem, st>>>((const bf16*)h, (const bf16*)hpre, gate, lse, D, (const bf16*)dout, (bf16*)dh, frames, L);
+  dim3 grid((unsigned)ceil_div(L > La ? L : La, BM), (unsigned)frames, 2);
+  kern<<<grid, NW * 32, smem, st>>>((const bf16*)h, (const bf16*)hpre, gate, lse, D, (const bf16*)dout, (bf16*)dh, frames, L, La);
   return check_launch("xmodal_global_bwd(tc)");
 }
 
@@ -376,13 +382,13 @@ static int bwd_launch(const void* h, const void* hpre, const float* gate, const 
 
 // entry points used by xmodal.cu's bf16 dispatch; return -1 for an unsupported rp
 int xmodal_global_fwd_bf16(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L,
-                           int rp, cudaStream_t st) {
+                           int La, int rp, cudaStream_t st) {
   // 4 warps (64 own rows) per CTA: measured against 8 and 2 warps at L = 3136 (32 clips): 5.1 / 5.7 / 5.5 ms forward,
   // 10.4 / 11.1 / 11.2 ms backward per step -- two block-wide barriers per 64-row tile are cheaper with fewer warps, and
   // the streamed tiles are L2 hits whichever CTA re-reads them
 #define XTC_FWD(RP_)                                                                               \
   case RP_:                                                                                        \
-    return xtc::fwd_launch<RP_, 4>(h, gate, out, attn_out, lse, frames, L, st);
+    return xtc::fwd_launch<RP_, 4>(h, gate, out, attn_out, lse, frames, L, La, st);
   switch (rp) {
     XTC_FWD(16) XTC_FWD(32) XTC_FWD(48) XTC_FWD(64) XTC_FWD(96)
     default: return -1;
@@ -391,10 +397,10 @@ int xmodal_global_fwd_bf16(const void* h, const float* gate, void* out, void* at
 }
 
 int xmodal_global_bwd_bf16(const void* h, const void* hpre, const float* gate, const float* lse, const float* D,
-                           const void* dout, void* dh, int64_t frames, int L, int rp, cudaStream_t st) {
+                           const void* dout, void* dh, int64_t frames, int L, int La, int rp, cudaStream_t st) {
 #define XTC_BWD(RP_)                                                                                   \
   case RP_:                                                                                            \
-    return xtc::bwd_launch<RP_, 4>(h, hpre, gate, lse, D, dout, dh, frames, L, st);
+    return xtc::bwd_launch<RP_, 4>(h, hpre, gate, lse, D, dout, dh, frames, L, La, st);
   switch (rp) {
     XTC_BWD(16) XTC_BWD(32) XTC_BWD(48) XTC_BWD(64) XTC_BWD(96)
     default: return -1;

@@ -34,8 +34,8 @@ _SIGNATURES = {
     "stgcma_temporal_attn_bwd": [_vp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp],
     "stgcma_xmodal_window_fwd": [_vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_xmodal_window_bwd": [_vp, _vp, _fp, _vp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
-    "stgcma_xmodal_global_fwd": [_vp, _fp, _vp, _vp, _fp, _i64, _i, _i, _i, _vp],
-    "stgcma_xmodal_global_bwd": [_vp, _vp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _vp],
+    "stgcma_xmodal_global_fwd": [_vp, _fp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _vp],
+    "stgcma_xmodal_global_bwd": [_vp, _vp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _vp],
     "stgcma_head_pool_fwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "stgcma_head_pool_bwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "stgcma_pack_params": [_vp, _i, _i, _vp],
@@ -255,14 +255,18 @@ def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, s
           ws, shift, rp, dt(h), cost=(16.0 * tok * ws * ws * (r or rp), _es(h) * 2 * tok * rp * 5))
 
 
-def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp, r=None):
-    _call("stgcma_xmodal_global_fwd", _p(h), _p(gate), _p(out), _p(attn_out), _p(lse), frames, L, rp, dt(h),
-          cost=(8.0 * frames * L * L * (r or rp), _es(h) * 2 * frames * L * rp * 3))
+def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp, r=None, La=None):
+    """La: rows per frame of the second modality when it differs from L (CLIP: 197 / 49); tensors are then the stacked
+    blocks [frames * L, rp] + [frames * La, rp]."""
+    La = L if La is None else La
+    _call("stgcma_xmodal_global_fwd", _p(h), _p(gate), _p(out), _p(attn_out), _p(lse), frames, L, La, rp, dt(h),
+          cost=(8.0 * frames * L * La * (r or rp), _es(h) * frames * (L + La) * rp * 3))
 
 
-def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp, r=None):
+def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp, r=None, La=None):
+    La = L if La is None else La
     _call("stgcma_xmodal_global_bwd", _p(h), _p(hpre), _p(gate), _p(attn_out), _p(lse), _p(dout), _p(dh), _p(dgate),
-          _p(work), frames, L, rp, dt(h), cost=(16.0 * frames * L * L * (r or rp), _es(h) * 2 * frames * L * rp * 5))
+          _p(work), frames, L, La, rp, dt(h), cost=(16.0 * frames * L * La * (r or rp), _es(h) * frames * (L + La) * rp * 5))
 
 
 def head_pool_fwd(xn, feat, frames, N, C):

@@ -275,24 +275,28 @@ def xmodal_window_bwd(h, hpre, gate, attn_out, dout, dh, dgate, frames, R, ws, s
     dgate.add_(ggate.to(dgate.dtype))
 
 
-def _xg(h, gate, frames, L, rp):
-    x = h.reshape(2, frames, L, rp)
-    ov, oa, a2v, v2a, lv, la = _xmodal(x[0], x[1], gate)
-    return torch.stack((ov, oa)), torch.stack((a2v, v2a)), torch.stack((lv, la))
+def _xg(h, gate, frames, L, rp, La=None):
+    """-> (out, attn_out, lse), each the video block followed by the audio block (flattened rows: La may differ from L)."""
+    La = L if La is None else La
+    h = h.reshape(-1, rp)
+    hv, ha = h[:frames * L].reshape(frames, L, rp), h[frames * L:].reshape(frames, La, rp)
+    ov, oa, a2v, v2a, lv, la = _xmodal(hv, ha, gate)
+    cat = lambda a, b: torch.cat((a.reshape(-1, rp), b.reshape(-1, rp)))
+    return cat(ov, oa), cat(a2v, v2a), torch.cat((lv.reshape(-1), la.reshape(-1)))
 
 
-def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp, r=None):
-    o, a, l = _xg(_c(h), _c(gate), frames, L, rp)
+def xmodal_global_fwd(h, gate, out, attn_out, lse, frames, L, rp, r=None, La=None):
+    o, a, l = _xg(_c(h), _c(gate), frames, L, rp, La)
     out.copy_(o.reshape(out.shape))
     attn_out.copy_(a.reshape(attn_out.shape))
     lse.copy_(l.reshape(lse.shape))
 
 
 @torch.enable_grad()
-def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp, r=None):
+def xmodal_global_bwd(h, hpre, gate, attn_out, lse, dout, dh, dgate, work, frames, L, rp, r=None, La=None):
     hh = _c(h).detach().clone().requires_grad_(True)
     gg = _c(gate).detach().clone().requires_grad_(True)
-    o, _, _ = _xg(hh, gg, frames, L, rp)
+    o, _, _ = _xg(hh, gg, frames, L, rp, La)
     gh, ggate = torch.autograd.grad(o, (hh, gg), _c(dout).reshape(o.shape))
     if hpre is not None:
         gh = gh * _dgelu(_c(hpre)).reshape(gh.shape)

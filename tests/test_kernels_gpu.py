@@ -440,6 +440,37 @@ def test_xmodal_global(frames, Ln, rp, r, spread, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("frames,Lv,La,rp,r", [(3, 197, 49, 48, 48), (2, 49, 197, 16, 12), (1, 130, 7, 32, 24), (2, 64, 65, 16, 16)])
+def test_xmodal_global_asymmetric(frames, Lv, La, rp, r, dtype):
+    """Different token counts per modality (CLIP ViT-B/16: 197 video / 49 audio tokens per frame, CLIP_AVE.py:380-397):
+    rows are the [frames * Lv] video block followed by the [frames * La] audio block."""
+    rows = frames * (Lv + La)
+    h = _h_inputs(rows, rp, r, dtype, 1)
+    hpre = rnd(rows, rp, dtype=dtype, seed=2)
+    gate = torch.tensor([0.7, 0.3], device="cuda")
+    nan = float("nan")
+    out, att = torch.full_like(h, nan), torch.full_like(h, nan)
+    lse = torch.full((rows,), nan, device="cuda")
+    L().xmodal_global_fwd(h, gate, out, att, lse, frames, Lv, rp, La=La)
+    r_o, r_a, r_l = (torch.empty(rows, rp, dtype=torch.float64), torch.empty(rows, rp, dtype=torch.float64),
+                     torch.empty(rows, dtype=torch.float64))
+    R.xmodal_global_fwd(cpu(h), cpu(gate), r_o, r_a, r_l, frames, Lv, rp, La=La)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert rel(out, r_o) < TOL[dtype] and rel(att, r_a) < TOL[dtype] and rel(lse, r_l) < TOL[dtype]
+    dout = rnd(rows, rp, dtype=dtype, seed=3)
+    dh = torch.full_like(h, nan)
+    dgate = torch.zeros(2, device="cuda")
+    work = torch.empty(rows, device="cuda")
+    L().xmodal_global_bwd(h, hpre, gate, att, lse, dout, dh, dgate, work, frames, Lv, rp, La=La)
+    r_dh, r_dg = torch.empty(rows, rp, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)
+    R.xmodal_global_bwd(cpu(h), cpu(hpre), cpu(gate), cpu(att), cpu(lse), cpu(dout), r_dh, r_dg, None, frames, Lv, rp, La=La)
+    assert torch.isfinite(dh.float()).all()
+    # r = 48 unscaled logits give near one-hot rows: the bf16 rounding of P shows (1.05e-2 measured at 197 x 49): north-star bar
+    assert rel(dh, r_dh) < (2e-2 if dtype == torch.bfloat16 and r >= 48 else TOL[dtype])
+    assert rel(dgate, r_dg) < max(TOL[dtype], 1e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_head_pool(dtype):
     frames, N, C = 5, 49, 768
     xn = rnd(2 * frames * N, C, dtype=dtype, seed=1)
