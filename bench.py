@@ -339,7 +339,7 @@ def reference(args):
     steps, warmup = max(1, min(args.steps, 4)), min(args.warmup, 1)
     cb = cpu_reference_run(args.model, steps=steps, warmup=warmup, clips=2)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": round(2 * 1e3 / cb["value"], 1),   # 2 clips per step "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": round(2 * 1e3 / cb["value"], 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD[args.model], "clips_per_step": 2, "frames": 10,
                        "note": "CPU reference arm: bounded sample of the same workload on the host cores; "
