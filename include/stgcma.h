@@ -225,6 +225,49 @@ typedef struct StgcmaAdamGroups {
 int stgcma_adam_step(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host, float grad_scale,
                      void* stream);
 
+/* ==== CLIP-ViT variant of the step (MM_CLIP_AVE, AVE/model/CLIP_AVE.py:716; BASELINE.json configs[1]) ================
+
+ * ---- multi-head attention core of nn.MultiheadAttention (CLIP_AVE.py:54, :106-108; no mask, no dropout) -------------
+ * o[:, h] = softmax(q_h k_h^T / sqrt(hd)) v_h per sequence and head; the packed in-projection and the out-projection
+ * around it are stgcma_gemm calls.  qkv [rows, 3*heads*hd], channel order [q | k | v] x heads x hd (in_proj_weight
+ * layout); out [rows, heads*hd]; lse fp32 [rows, heads] (natural log, saved for backward).
+ * Sequences: n_seq sequences of seq_len tokens; token i of sequence s is row
+ *     (s / inner) * seq_len * inner + (s % inner) + i * inner
+ *   inner = 1: contiguous sequences = the spatial attention over the N tokens of a frame (:385, :388)
+ *   inner = N: the temporal attention 'n (b t) d -> t (b n) d' (:369-377): sequence = the T frames of one (clip, token)
+ *              of a [clips, T, N] row layout, n_seq = clips * N, seq_len = T.
+ * bf16: hd in {16, 32, 64, 96, 128}, sequences must fit shared memory (seq_len <= ~300); fp32: hd <= 128.
+ * bwd writes dqkv [rows, 3*heads*hd]; `work` = fp32 [rows, heads] scratch owned by the caller (bf16 mode).          */
+int stgcma_mha_fwd(const void* qkv, void* out, float* lse, int64_t n_seq, int seq_len, int inner, int heads, int hd,
+                   int dtype, void* stream);
+int stgcma_mha_bwd(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, float* work,
+                   int64_t n_seq, int seq_len, int inner, int heads, int hd, int dtype, void* stream);
+
+/* ---- patchify: conv1 / conv1_audio, kernel = stride = P, no bias (CLIP_AVE.py:728,:741,:1091,:1107) as a gather in
+ * front of stgcma_gemm.  img fp32 [B, Cin, T, H, W] (audio: Cin = 1, [B, 1, T, 102, 128]);
+ * out[((b*T + t)*Hp + py)*Wp + px][(c*P + ky)*P + kx] = img[b][c][t][py*P + ky][px*P + kx], Hp = (H-P)/P + 1 (rows
+ * that do not fill a patch are dropped, like the convolution); row stride ldo >= Cin*P*P elements (pad columns are
+ * not written).                                                                                                    */
+int stgcma_im2col(const float* img, void* out, int B, int Cin, int T, int H, int W, int P, int64_t ldo, int dtype,
+                  void* stream);
+/* ---- token assembly (CLIP_AVE.py:1094-1103): x0[bt][0] = class_embedding, x0[bt][1 + p] = patches[bt][p], then
+ * + positional_embedding[i] + temporal_embedding[bt % T].  patches [BT*(N-1), D] (`dtype`), cls fp32 [D], pos fp32
+ * [N, D], temb fp32 [T, D]; x0 fp32 [BT*N, D] (the residual stream; ln_pre follows as stgcma_layernorm_fwd).        */
+int stgcma_clip_embed_fwd(const void* patches, const float* cls, const float* pos, const float* temb, float* x0,
+                          int64_t BT, int T, int N, int D, int dtype, void* stream);
+/* gradient of the trainable temporal embedding (CLIP_AVE.py:749-752): dtemb[t] += sum_{b, i} dx0[(b*T + t)*N + i]  */
+int stgcma_clip_temb_bwd(const float* dx0, float* dtemb, int64_t B, int T, int N, int D, void* stream);
+/* ---- head input (CLIP_AVE.py:1124-1137): ln_post (TRAINABLE affine) on the class-token row of every frame, then
+ * cat(audio, video).  x fp32 stream: [frames, Nv, D] video block followed by [frames, Na, D] audio block;
+ * feat fp32 [frames, 2D] = [LN(x_a[f, 0]) | LN(x_v[f, 0])]; mean / rstd fp32 [2*frames] (video rows then audio rows).
+ * bwd: writes ONLY the class-token rows of dx and of its optional copy dx_copy in the activation type `dtype` (the
+ * caller zero-fills both), accumulates dgamma / dbeta fp32 [D].                                                    */
+int stgcma_cls_ln_fwd(const float* x, const float* gamma, const float* beta, float* feat, float* mean, float* rstd,
+                      int64_t frames, int Nv, int Na, int D, void* stream);
+int stgcma_cls_ln_bwd(const float* dfeat, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      float* dx, void* dx_copy, float* dgamma, float* dbeta, int64_t frames, int Nv, int Na, int D,
+                      int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

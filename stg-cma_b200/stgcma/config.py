@@ -49,3 +49,56 @@ PRESETS = {
     "swin_l": dict(embed_dim=192, depths=[2, 2, 18, 2], num_heads=[6, 12, 24, 48],
                    adapter_mlp_ratio=[0.5, 0.25, 0.125, 0.0625]),
 }
+
+
+@dataclass
+class ClipAVEConfig:
+    """Static shape description of `MM_CLIP_AVE` (reference ctor arguments, AVE/model/CLIP_AVE.py:718-719,
+    AVE/run_adapt_ave29.py:132-139).  ViT-B/16 as the reference runs it: 12 layers, D = 768, EIGHT heads of 96."""
+    label_dim: int = 29
+    input_resolution: int = 224
+    audio_length: int = 1024        # fbank target_length; the model sees [B, T, audio_length // 10, 128]
+    num_frames: int = 10
+    patch_size: int = 16
+    embed_dim: int = 768
+    layers: int = 12
+    heads: int = 8
+    adapter_ratio: float = 0.0625   # Adapter(mlp_ratio=0.0625), CLIP_AVE.py:14
+
+    @property
+    def grid_v(self):
+        return self.input_resolution // self.patch_size
+
+    @property
+    def nv(self):                   # video tokens per frame incl. the class token
+        return self.grid_v ** 2 + 1
+
+    @property
+    def audio_shape(self):          # (H, W) of one audio image: [audio_length / 10 time steps, 128 mel bins]
+        return int(self.audio_length * (1 / 10)), 128
+
+    @property
+    def grid_a(self):               # conv output (rows, cols) on an [H, W] audio image, kernel = stride = patch
+        h, w = self.audio_shape
+        return (h - self.patch_size) // self.patch_size + 1, (w - self.patch_size) // self.patch_size + 1
+
+    @property
+    def na(self):
+        gh, gw = self.grid_a
+        return gh * gw + 1
+
+    @property
+    def r(self):
+        return int(self.embed_dim * self.adapter_ratio)
+
+    @property
+    def head_dim(self):
+        return self.embed_dim // self.heads
+
+
+CLIP_PRESETS = {
+    # BASELINE.json configs[1]: ViT-B/16 exactly as run_adapt_ave29.py:132-139 builds it
+    "clip_b16": dict(input_resolution=224, patch_size=16, embed_dim=768, layers=12, heads=8),
+    # ViT-L/14 (run_adapt_ave29.py:141-148)
+    "clip_l14": dict(input_resolution=224, patch_size=14, embed_dim=1024, layers=24, heads=16),
+}

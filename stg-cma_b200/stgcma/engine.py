@@ -657,7 +657,10 @@ class SwinAVEEngine:
                     dfpre = buf(f"dfpre{s}", M, hid)
                     L_.gemm(dy, f["fc2_wt"], dfpre, M, hid, C, aux=slot(k + "fpre"), epi=L_.EPI_DGELU)
                     L_.gemm(dfpre, f["fc1_wt"], dxn, M, C, hid)
-                dx2, dx2b = buf(f"dD{s}", M, C, dtype=sdt), buf(f"dDb{s}", M, C)
+                # the three sub-blocks rotate over three buffer pairs (G -> dE, S -> dB, T -> dD): the side-stream dW kernels
+                # launched above still read dxb, which after a (T) sub-block IS dDb -- writing this sub-block's result there
+                # would race with them (they are joined only at the start of the next sub-block)
+                dx2, dx2b = buf(f"dE{s}", M, C, dtype=sdt), buf(f"dEb{s}", M, C)
                 L_.layernorm_bwd(dxn, sv[k + "x2"], slot(k + "g_mean"), slot(k + "g_rstd"), f["n2g"], dx, dx2, M, C, dx_copy=dx2b)
                 # ---------------- (S) backward: dx2 ----------------
                 join_side()

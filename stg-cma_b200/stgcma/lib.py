@@ -40,6 +40,13 @@ _SIGNATURES = {
     "stgcma_head_pool_bwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "stgcma_pack_params": [_vp, _i, _i, _vp],
     "stgcma_adam_step": [_vp, _i, _vp, ctypes.c_float, _vp],
+    "stgcma_mha_fwd": [_vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_mha_bwd": [_vp, _vp, _fp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
+    "stgcma_im2col": [_fp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i, _vp],
+    "stgcma_clip_embed_fwd": [_vp, _fp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _vp],
+    "stgcma_clip_temb_bwd": [_fp, _fp, _i64, _i, _i, _i, _vp],
+    "stgcma_cls_ln_fwd": [_fp, _fp, _fp, _fp, _fp, _fp, _i64, _i, _i, _i, _vp],
+    "stgcma_cls_ln_bwd": [_fp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _vp],
 }
 EXPORTS = ["stgcma_last_error", "stgcma_version"] + list(_SIGNATURES)
 
@@ -275,6 +282,46 @@ def head_pool_fwd(xn, feat, frames, N, C):
 
 def head_pool_bwd(dfeat, dxn, frames, N, C):
     _call("stgcma_head_pool_bwd", _p(dfeat), _p(dxn), frames, N, C, dt(dxn), cost=(0.0, _es(dxn) * 2 * frames * (N + 1) * C))
+
+
+# ---- CLIP-ViT variant (MM_CLIP_AVE) ------------------------------------------------------------------------
+def mha_fwd(qkv, out, lse, n_seq, seq_len, inner, heads, hd):
+    """Attention core of nn.MultiheadAttention; `qkv` / `out` / `lse` may be row-offset views (one modality)."""
+    tok = n_seq * seq_len
+    _call("stgcma_mha_fwd", _p(qkv), _p(out), _p(lse), n_seq, seq_len, inner, heads, hd, dt(qkv),
+          cost=(4.0 * tok * seq_len * heads * hd, _es(qkv) * tok * 4 * heads * hd))
+
+
+def mha_bwd(qkv, out, lse, dout, dqkv, work, n_seq, seq_len, inner, heads, hd):
+    tok = n_seq * seq_len
+    _call("stgcma_mha_bwd", _p(qkv), _p(out), _p(lse), _p(dout), _p(dqkv), _p(work), n_seq, seq_len, inner, heads, hd,
+          dt(qkv), cost=(10.0 * tok * seq_len * heads * hd, _es(qkv) * tok * 8 * heads * hd))
+
+
+def im2col(img, out, B, Cin, T, H, W, P, ldo=None):
+    K = Cin * P * P
+    rows = B * T * ((H - P) // P + 1) * ((W - P) // P + 1)
+    _call("stgcma_im2col", _p(img), _p(out), B, Cin, T, H, W, P, K if ldo is None else ldo, dt(out),
+          cost=(0.0, rows * K * (4.0 + _es(out))))
+
+
+def clip_embed_fwd(patches, cls, pos, temb, x0, BT, T, N, D):
+    _call("stgcma_clip_embed_fwd", _p(patches), _p(cls), _p(pos), _p(temb), _p(x0), BT, T, N, D, dt(patches),
+          cost=(0.0, BT * N * D * (4.0 + _es(patches))))
+
+
+def clip_temb_bwd(dx0, dtemb, B, T, N, D):
+    _call("stgcma_clip_temb_bwd", _p(dx0), _p(dtemb), B, T, N, D, cost=(0.0, 4.0 * B * T * N * D))
+
+
+def cls_ln_fwd(x, gamma, beta, feat, mean, rstd, frames, Nv, Na, D):
+    _call("stgcma_cls_ln_fwd", _p(x), _p(gamma), _p(beta), _p(feat), _p(mean), _p(rstd), frames, Nv, Na, D,
+          cost=(0.0, 16.0 * frames * D))
+
+
+def cls_ln_bwd(dfeat, x, mean, rstd, gamma, dx, dgamma, dbeta, frames, Nv, Na, D, dx_copy=None):
+    _call("stgcma_cls_ln_bwd", _p(dfeat), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dx_copy), _p(dgamma), _p(dbeta),
+          frames, Nv, Na, D, dt(dx_copy if dx_copy is not None else dx), cost=(0.0, 24.0 * frames * D))
 
 
 PACK_ENTRY = struct.Struct("<QQiiqqii")  # mirrors StgcmaPackEntry (48 bytes)

@@ -314,6 +314,97 @@ def head_pool_bwd(dfeat, dxn, frames, N, C):
     dxn.reshape(2, frames, N, C).copy_(torch.stack((d[:, 1], d[:, 0]))[:, :, None, :].expand(2, frames, N, C))
 
 
+# ---- CLIP-ViT variant ---------------------------------------------------------------------------
+def _seq_rows(n_seq, seq_len, inner, device):
+    """[n_seq, seq_len] row index of token i of sequence s (include/stgcma.h, stgcma_mha_fwd)."""
+    s = torch.arange(n_seq, device=device).view(-1, 1)
+    i = torch.arange(seq_len, device=device).view(1, -1)
+    return (s // inner) * seq_len * inner + (s % inner) + i * inner
+
+
+def _mha(qkv, n_seq, seq_len, inner, heads, hd):
+    D = heads * hd
+    rows = n_seq * seq_len
+    idx = _seq_rows(n_seq, seq_len, inner, qkv.device)
+    x = qkv.reshape(-1, 3 * D)[:rows][idx]                           # [n_seq, seq_len, 3D]
+    q, k, v = (t.reshape(n_seq, seq_len, heads, hd).transpose(1, 2) for t in x.split(D, dim=-1))
+    s = (q * hd ** -0.5) @ k.transpose(-1, -2)
+    o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(n_seq, seq_len, D)
+    lse = torch.logsumexp(s, -1).transpose(1, 2)                     # [n_seq, seq_len, heads]
+    inv = torch.empty(rows, dtype=torch.long, device=qkv.device)
+    inv[idx.reshape(-1)] = torch.arange(rows, device=qkv.device)
+    return o.reshape(rows, D)[inv], lse.reshape(rows, heads)[inv]
+
+
+def mha_fwd(qkv, out, lse, n_seq, seq_len, inner, heads, hd):
+    rows = n_seq * seq_len
+    o, l = _mha(_c(qkv), n_seq, seq_len, inner, heads, hd)
+    out.reshape(-1, heads * hd)[:rows].copy_(o)
+    lse.reshape(-1, heads)[:rows].copy_(l)
+
+
+@torch.enable_grad()
+def mha_bwd(qkv, out, lse, dout, dqkv, work, n_seq, seq_len, inner, heads, hd):
+    rows, D = n_seq * seq_len, heads * hd
+    q = _c(qkv).reshape(-1, 3 * D)[:rows].detach().clone().requires_grad_(True)
+    o, _ = _mha(q, n_seq, seq_len, inner, heads, hd)
+    (g,) = torch.autograd.grad(o, q, _c(dout).reshape(-1, D)[:rows])
+    dqkv.reshape(-1, 3 * D)[:rows].copy_(g)
+
+
+def im2col(img, out, B, Cin, T, H, W, P, ldo=None):
+    Hp, Wp = (H - P) // P + 1, (W - P) // P + 1
+    K = Cin * P * P
+    ldo = K if ldo is None else ldo
+    x = _c(img).reshape(B, Cin, T, H, W)[:, :, :, :Hp * P, :Wp * P].reshape(B, Cin, T, Hp, P, Wp, P)
+    x = x.permute(0, 2, 3, 5, 1, 4, 6).reshape(B * T * Hp * Wp, K)
+    _view2d(out, x.shape[0], K, ldo).copy_(x)
+
+
+def clip_embed_fwd(patches, cls, pos, temb, x0, BT, T, N, D):
+    p = _c(patches).reshape(BT, N - 1, D)
+    x = torch.cat((_c(cls).reshape(1, 1, D).expand(BT, 1, D), p), 1) + _c(pos).reshape(1, N, D)
+    x = x.reshape(BT // T, T, N, D) + _c(temb).reshape(1, T, 1, D)
+    x0.reshape(BT, N, D).copy_(x.reshape(BT, N, D))
+
+
+def clip_temb_bwd(dx0, dtemb, B, T, N, D):
+    dtemb.reshape(T, D).add_(_c(dx0).reshape(B, T, N, D).sum((0, 2)).to(dtemb.dtype))
+
+
+def _cls_rows(x, frames, Nv, Na, D):
+    x = x.reshape(-1, D)
+    return torch.cat((x[:frames * Nv].reshape(frames, Nv, D)[:, 0], x[frames * Nv:].reshape(frames, Na, D)[:, 0]))   # [2*frames, D]
+
+
+def cls_ln_fwd(x, gamma, beta, feat, mean, rstd, frames, Nv, Na, D):
+    xr = _cls_rows(_c(x), frames, Nv, Na, D)
+    mu = xr.mean(-1)
+    rs = torch.rsqrt(((xr - mu[:, None]) ** 2).mean(-1) + 1e-5)
+    y = (xr - mu[:, None]) * rs[:, None] * _c(gamma) + _c(beta)
+    feat.reshape(frames, 2 * D).copy_(torch.cat((y[frames:], y[:frames]), -1))
+    mean.copy_(mu)
+    rstd.copy_(rs)
+
+
+def cls_ln_bwd(dfeat, x, mean, rstd, gamma, dx, dgamma, dbeta, frames, Nv, Na, D, dx_copy=None):
+    xr = _cls_rows(_c(x), frames, Nv, Na, D)
+    df = _c(dfeat).reshape(frames, 2 * D)
+    dy = torch.cat((df[:, D:], df[:, :D]))                            # video rows then audio rows
+    xh = (xr - _c(mean)[:, None]) * _c(rstd)[:, None]
+    g = dy * _c(gamma)
+    d = _c(rstd)[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    dxf = dx.reshape(-1, D)
+    dxf[:frames * Nv].reshape(frames, Nv, D)[:, 0] = d[:frames].to(dx.dtype)
+    dxf[frames * Nv:].reshape(frames, Na, D)[:, 0] = d[frames:].to(dx.dtype)
+    if dx_copy is not None:
+        cf = dx_copy.reshape(-1, D)
+        cf[:frames * Nv].reshape(frames, Nv, D)[:, 0] = d[:frames].to(dx_copy.dtype)
+        cf[frames * Nv:].reshape(frames, Na, D)[:, 0] = d[frames:].to(dx_copy.dtype)
+    dgamma.add_((dy * xh).sum(0).to(dgamma.dtype))
+    dbeta.add_(dy.sum(0).to(dbeta.dtype))
+
+
 # ---- parameter packing (host memory only: used by the CPU fake backend) ------------------------
 _DT = {0: torch.float32, 1: torch.bfloat16, 2: torch.float64}
 _CT = {torch.float32: ctypes.c_float, torch.float64: ctypes.c_double}
@@ -354,7 +445,8 @@ def install_fake_backend(monkeypatch, lib_module):
     me = sys.modules[__name__]
     for name in ("patch_embed_fwd", "layernorm_fwd", "layernorm_bwd", "gemm", "gemm_tn", "mlp_fwd", "mlp_bwd", "window_attn_fwd",
                  "window_attn_bwd", "temporal_attn_fwd", "temporal_attn_bwd", "xmodal_window_fwd", "xmodal_window_bwd",
-                 "xmodal_global_fwd", "xmodal_global_bwd", "head_pool_fwd", "head_pool_bwd", "pack_params"):
+                 "xmodal_global_fwd", "xmodal_global_bwd", "head_pool_fwd", "head_pool_bwd", "pack_params", "mha_fwd", "mha_bwd",
+                 "im2col", "clip_embed_fwd", "clip_temb_bwd", "cls_ln_fwd", "cls_ln_bwd"):
         monkeypatch.setattr(lib_module, name, getattr(me, name))
     monkeypatch.setattr(lib_module, "require_device", lambda *t: None)
     monkeypatch.setattr(lib_module, "dt", lambda d: {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}[

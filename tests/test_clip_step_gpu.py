@@ -1,0 +1,164 @@
+"""End-to-end parity of the CLIP-ViT CUDA train step (model/CLIP_AVE.py -> libstgcma.so) on a real B200
+(BASELINE.json configs[1]; SURVEY.md 8a row "CLIP: ResidualAttentionBlock.forward fusion").
+
+Bars as in test_step_gpu.py: logits and every trainable gradient within 1e-3 (fp32 check mode, max-abs metric) / 2e-2
+(bf16 production mode: max-abs for the logits, per-tensor relative L2 for the gradients) of
+  (a) the oracle run here on the CPU in fp64 and
+  (b) the fixtures in tests/golden/clip_*.pt produced by the UNMODIFIED reference `MM_CLIP_AVE`
+      (oracle/make_clip_goldens.py), including the full-width ViT-B/16 geometry (197 / 49 tokens, D = 768, 8 heads).
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import clip_ave_oracle as C
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+TINY = dict(label_dim=7, input_resolution=64, audio_length=480, num_frames=3, patch_size=16, embed_dim=64, layers=2, heads=4)
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def build(kw, mode, dtype, sd, drop_path_rate=0.0):
+    import model
+    m = model.CLIP_AVE.MM_CLIP_AVE(label_dim=kw["label_dim"], input_resolution=kw["input_resolution"],
+                                   audio_length=kw["audio_length"], num_video_frames=kw["num_frames"],
+                                   patch_size=kw["patch_size"], embed_dim=kw["embed_dim"], layers=kw["layers"],
+                                   heads=kw["heads"], drop_path_rate=drop_path_rate, pretrained=None, ftmode=mode,
+                                   compute_dtype=dtype).cuda()
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    m.mlp_head[1].eval()
+    for n, p in m.named_parameters():
+        p.requires_grad_(C.is_trainable(n))
+    return m
+
+
+def step(m, a, v, labels, mode):
+    m.zero_grad(set_to_none=True)
+    out = m(a.cuda(), v.cuda(), mode)
+    loss = torch.nn.CrossEntropyLoss()(out, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    return out.detach().cpu(), float(loss), {n: p.grad.detach().cpu() for n, p in m.named_parameters()
+                                             if p.requires_grad and p.grad is not None}
+
+
+def rel(got, ref):
+    return float((got.double() - ref.double()).abs().max() / ref.double().abs().max().clamp_min(1e-30))
+
+
+def rel_l2(got, ref):
+    return float((got.double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
+
+
+def check_grads(g, ref_g, tol, metric):
+    bad = []
+    gates = [n for n in ref_g if "gate_" in n]
+    for n in ref_g:
+        if n in gates:
+            continue
+        e = metric(g[n], ref_g[n])
+        if not e < tol:
+            bad.append((n, e))
+    if gates:   # 1-element tensors with heavy cancellation: compared as one stacked vector (test_step_gpu.py)
+        e = metric(torch.stack([g[n].reshape(()) for n in gates]), torch.stack([ref_g[n].reshape(()) for n in gates]))
+        if not e < tol:
+            bad.append(("gates(stacked)", e))
+    assert not bad, f"{len(bad)} gradient tensors beyond {tol}: {sorted(bad, key=lambda t: -t[1])[:8]}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["fusion", "multimodal"])
+def test_tiny_step_vs_oracle(mode, dtype):
+    cfg = C.ClipAVEConfig(**TINY)
+    sd = C.make_state(cfg, seed=3, bf16_exact=True)
+    a, v, labels = C.make_inputs(cfg, 2, seed=3)
+    r_out, r_loss, r_g = C.train_step({k: t.double() for k, t in sd.items()}, a.double(), v.double(), labels.double(), cfg, mode)
+    m = build(TINY, mode, dtype, sd)
+    out, loss, g = step(m, a, v, labels, mode)
+    assert out.dtype == torch.float32
+    assert rel(out, r_out) < TOL[dtype]
+    assert abs(loss - float(r_loss)) < TOL[dtype] * max(1.0, abs(float(r_loss)))
+    assert set(r_g) <= set(g)
+    check_grads(g, r_g, TOL[dtype], rel if dtype == torch.float32 else rel_l2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["clip_tiny_fusion", "clip_tiny_multimodal", "clip_b16_L2_T2_fusion"])
+def test_step_vs_reference_golden(name, dtype):
+    fx = torch.load(os.path.join(GOLD, name + ".pt"))
+    cfg = C.ClipAVEConfig(**fx["cfg"])
+    sd = C.make_state(cfg, seed=fx["seed"], **fx["state_kw"])
+    a, v, labels = C.make_inputs(cfg, fx["batch"], seed=fx["seed"])
+    m = build(fx["cfg"], fx["mode"], dtype, sd)
+    out, loss, g = step(m, a, v, labels, fx["mode"])
+    assert rel(out, fx["logits"]) < TOL[dtype]
+    assert abs(loss - float(fx["loss"])) < TOL[dtype] * max(1.0, abs(float(fx["loss"])))
+    check_grads(g, fx["grads"], TOL[dtype], rel_l2)
+    if dtype == torch.float32:
+        check_grads(g, fx["grads"], TOL[dtype], rel)
+    # tensors too large for the fixture: L2 norm and a 64-element probe
+    from oracle.make_goldens import probe_index
+    bad = []
+    for n, nrm in fx["grad_norm"].items():
+        if n in fx["grads"]:
+            continue
+        got = g[n].double()
+        probe = got.reshape(-1)[probe_index(got.numel())]
+        scale = nrm / max(got.numel(), 1) ** 0.5
+        if abs(float(got.norm()) - nrm) > TOL[dtype] * nrm or float((probe - fx["grad_probe"][n]).abs().max()) > 10 * TOL[dtype] * scale:
+            bad.append(n)
+    assert not bad, bad[:8]
+
+
+def test_drop_path_and_dropout_replay():
+    """Stochastic layers on the GPU: the engine draws the masks, the oracle replays them (fp32 mode)."""
+    cfg = C.ClipAVEConfig(**TINY)
+    sd = C.make_state(cfg, seed=5)
+    a, v, labels = C.make_inputs(cfg, 2, seed=5)
+    m = build(TINY, "fusion", torch.float32, sd, drop_path_rate=0.5)
+    m.mlp_head[1].train()
+    torch.manual_seed(0)
+    out = m(a.cuda(), v.cuda(), "fusion")
+    saved = m.engine().saved_masks(out.grad_fn.saved)
+    masks = {i: dict(v=d["v"].repeat(2).cpu().double(), a=d["a"].repeat(2).cpu().double()) for i, d in saved["dp"].items()}
+    keep = saved["keepmask"].cpu().double()
+    loss = torch.nn.CrossEntropyLoss()(out, labels.cuda())
+    loss.backward()
+    r_out, _, r_g = C.train_step({k: t.double() for k, t in sd.items()}, a.double(), v.double(), labels.double(), cfg, "fusion",
+                                 drop_masks=masks, head_keep=keep)
+    assert rel(out.detach().cpu(), r_out) < 1e-3
+    check_grads({n: p.grad.cpu() for n, p in m.named_parameters() if p.requires_grad}, r_g, 1e-3, rel)
+
+
+def test_full_width_properties():
+    """ViT-B/16 geometry, 3 layers, T = 10, B = 2 in bf16: properties that need no oracle."""
+    kw = dict(label_dim=29, input_resolution=224, audio_length=1024, num_frames=10, patch_size=16, embed_dim=768, layers=3, heads=8)
+    cfg = C.ClipAVEConfig(**kw)
+    sd = C.make_state(cfg, seed=7)
+    a, v, labels = C.make_inputs(cfg, 2, seed=7)
+    m = build(kw, "fusion", torch.bfloat16, sd)
+    out2, _, g2 = step(m, a, v, labels, "fusion")
+    assert torch.isfinite(out2).all() and all(torch.isfinite(t).all() for t in g2.values())
+    with torch.no_grad():
+        again = m(a.cuda(), v.cuda(), "fusion").cpu()
+    assert torch.equal(again, out2)                                   # (1) deterministic forward
+    with torch.no_grad():
+        out1 = m(a[:1].cuda(), v[:1].cuda(), "fusion").cpu()
+    assert rel(out1, out2[:10]) < 1e-6 or torch.equal(out1, out2[:10])   # (2) clips are independent (the DP partition)
+    m.zero_grad(set_to_none=True)
+    out = m(a.cuda(), v.cuda(), "fusion")
+    (8.0 * torch.nn.CrossEntropyLoss()(out, labels.cuda())).backward()
+    for n, p in m.named_parameters():                                 # (3) backward linear in dlogits
+        if p.requires_grad:
+            assert rel(p.grad.cpu(), 8.0 * g2[n]) < 2e-3, n
+    with torch.no_grad():                                             # (4) zero gates: fusion == multimodal
+        for n, p in m.named_parameters():
+            if "gate_" in n:
+                p.zero_()
+        f0 = m(a.cuda(), v.cuda(), "fusion").cpu()
+        mm = m(a.cuda(), v.cuda(), "multimodal").cpu()
+    assert rel(f0, mm) < 1e-6 or torch.equal(f0, mm)
