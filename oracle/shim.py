@@ -7,9 +7,11 @@ from timm (`Swin_AVE.py:1,5`: DropPath, to_2tuple, trunc_normal_); `clip` is tou
 when a pretrained path is given (`CLIP_AVE.py:818`) and `loratorch` is imported but unused
 (`CLIP_AVE.py:8`).
 
-/root/reference exists only in the build container; nothing run on the GPU box may call
-`load_reference()`.  It is used by `oracle/make_goldens.py` and
-`oracle/validate_oracle.py` to pin the oracle restatement to the real reference.
+/root/reference exists only in the build container.  `oracle/build_ref.py` stages verbatim copies of the files
+the tests and the baseline arms execute in the git-ignored `oracle/_ref/`, which travels to the GPU box: when
+/root/reference is absent `load_reference()` reads from there.  Used by `oracle/make_goldens.py`,
+`oracle/validate_oracle.py` (pin the oracle restatement to the real reference), tests/test_reference_gpu.py and
+the `--impl reference` / `--impl eager` arms of bench.py.
 """
 import importlib.util
 import os
@@ -20,6 +22,15 @@ import torch
 import torch.nn as nn
 
 REFERENCE_ROOT = os.environ.get("STGCMA_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    """The reference checkout when it exists (build container), else the staged copy oracle/_ref (GPU box), else None."""
+    for root in (REFERENCE_ROOT, STAGED_ROOT):
+        if os.path.isfile(os.path.join(root, "AVE", "model", "Swin_AVE.py")):
+            return root
+    return None
 
 
 class _DropPath(nn.Module):
@@ -65,7 +76,7 @@ def install_shims():
 
 
 def reference_available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "AVE", "model", "Swin_AVE.py"))
+    return reference_root() is not None
 
 
 def load_reference(relpath="AVE/model/Swin_AVE.py", modname="_ref_Swin_AVE"):
@@ -73,9 +84,17 @@ def load_reference(relpath="AVE/model/Swin_AVE.py", modname="_ref_Swin_AVE"):
     if modname in sys.modules:
         return sys.modules[modname]
     install_shims()
-    path = os.path.join(REFERENCE_ROOT, relpath)
+    path = os.path.join(reference_root(), relpath)
     spec = importlib.util.spec_from_file_location(modname, path)
     mod = importlib.util.module_from_spec(spec)
     sys.modules[modname] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_caller():
+    """The UNCHANGED caller `AVE/traintest_adapt_ave29.py` (train / validate) with its `from utilities import *`."""
+    root = reference_root()
+    if root not in sys.path:
+        sys.path.insert(0, root)          # `utilities` is a top-level package of the reference checkout
+    return load_reference("AVE/traintest_adapt_ave29.py", "_ref_traintest_adapt_ave29")

@@ -126,7 +126,7 @@ def profile_stop():
     return out
 
 
-def _call(name, *args, cost=(0.0, 0.0)):
+def _call(name, *args, cost=(0.0, 0.0), tag=""):
     global _launches
     lib = load()
     stream = _stream()
@@ -138,7 +138,7 @@ def _call(name, *args, cost=(0.0, 0.0)):
         raise StgcmaError(f"{name} failed ({rc}): {lib.stgcma_last_error().decode()}")
     if _prof is not None:
         e1.record()
-        _prof.append((name, e0, e1, float(cost[0]), float(cost[1])))
+        _prof.append((name + tag, e0, e1, float(cost[0]), float(cost[1])))
     _launches += 1
 
 
@@ -197,7 +197,7 @@ def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, 
           K, K if lda is None else lda, K if ldw is None else ldw, N if ldo is None else ldo, groups, epi, dt(A), dt(out),
           cost=(2.0 * M * N * K, _es(A) * (M * K + groups * N * K + M * N * (
               0.0 + (res2 is not None) + (aux is not None) + (out_pre is not None))) + _es(out) * M * N * (
-              1.0 + (res1 is not None))))
+              1.0 + (res1 is not None))), tag="[K<=192]" if K <= 192 else "[K>=256]")
 
 
 def mlp_fused_ok(C, H, rp, dtype, backward=True):

@@ -31,16 +31,22 @@ def randomize_(model, seed=0):
                 p.copy_(torch.randn(p.shape, generator=g) * 0.02)
             elif "gate_" in name:
                 p.copy_(0.25 + 0.5 * torch.rand(p.shape, generator=g))
-            elif "norm" in name and name.endswith("weight"):
+            elif ("norm" in name or ".ln_" in name or name.startswith("ln_")) and name.endswith("weight"):
                 p.copy_(1.0 + 0.05 * torch.randn(p.shape, generator=g))
     return model
 
 
 def make_clips(cfg, batch, seed=0, pin=False):
     g = torch.Generator().manual_seed(1000 + seed)
-    S, T = cfg.img_size, cfg.num_frames
-    v = torch.randn(batch, 3, T, S, S, generator=g)
-    a = torch.randn(batch, T, S, S, generator=g)
+    T = cfg.num_frames
+    if hasattr(cfg, "audio_shape"):      # CLIP path: audio is the [audio_length / 10, 128] fbank slice per frame
+        S = cfg.input_resolution
+        v = torch.randn(batch, 3, T, S, S, generator=g)
+        a = torch.randn(batch, T, *cfg.audio_shape, generator=g)
+    else:
+        S = cfg.img_size
+        v = torch.randn(batch, 3, T, S, S, generator=g)
+        a = torch.randn(batch, T, S, S, generator=g)
     labels = torch.softmax(torch.randn(batch * T, cfg.label_dim, generator=g), -1)
     if pin:
         v, a, labels = v.pin_memory(), a.pin_memory(), labels.pin_memory()
