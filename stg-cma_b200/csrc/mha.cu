@@ -45,11 +45,14 @@ template <int HD>
 __device__ __forceinline__ void load_tile(uint8_t* tile, const bf16* __restrict__ base, int64_t ld, const Seq& sq, int64_t s,
                                           int i0, int nrows, int tid, int nthr) {
   constexpr int CH = Cfg<HD>::CH, LD = Cfg<HD>::LD;
+  const bool live = s < sq.n_seq;
+  const bf16* row0 = base + (live ? sq.row(s, 0) : 0) * ld;      // one 64-bit division per call, not per 16-byte chunk
+  const int64_t step = (int64_t)sq.inner * ld;
   for (int e = tid; e < nrows * CH; e += nthr) {
     const int r = e / CH, c = e - r * CH;
     uint8_t* dst = tile + r * LD + c * 16;
     const int i = i0 + r;
-    if (i < sq.seq_len && s < sq.n_seq) cp_async16(dst, base + sq.row(s, i) * ld + c * 8);
+    if (live && i < sq.seq_len) cp_async16(dst, row0 + i * step + c * 8);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
 }
@@ -59,10 +62,12 @@ template <int HD>
 __device__ __forceinline__ void store_tile(const uint8_t* tile, bf16* __restrict__ base, int64_t ld, const Seq& sq, int64_t s,
                                            int i0, int lane) {
   constexpr int CH = Cfg<HD>::CH, LD = Cfg<HD>::LD;
+  bf16* row0 = base + sq.row(s, 0) * ld;
+  const int64_t step = (int64_t)sq.inner * ld;
   for (int e = lane; e < 16 * CH; e += 32) {
     const int r = e / CH, c = e - r * CH;
     const int i = i0 + r;
-    if (i < sq.seq_len) *reinterpret_cast<uint4*>(base + sq.row(s, i) * ld + c * 8) = *reinterpret_cast<const uint4*>(tile + r * LD + c * 16);
+    if (i < sq.seq_len) *reinterpret_cast<uint4*>(row0 + i * step + c * 8) = *reinterpret_cast<const uint4*>(tile + r * LD + c * 16);
   }
 }
 
@@ -647,6 +652,10 @@ static int check_args(const char* what, int64_t n_seq, int seq_len, int inner, i
 }
 
 }  // namespace mha
+
+// temporal_tc.cu: whole-sequence-in-one-tile kernels for T <= 16 frames of a [clips, T, tokens] layout (-1: not covered)
+int temporal_mha_fwd_bf16(const void* qkv, void* out, float* lse, int B, int T, int L, int heads, int hd, cudaStream_t st);
+int temporal_mha_bwd_bf16(const void* qkv, const void* dout, void* dqkv, int B, int T, int L, int heads, int hd, cudaStream_t st);
 }  // namespace stgcma
 
 using namespace stgcma;
@@ -677,6 +686,11 @@ extern "C" int stgcma_mha_fwd(const void* qkv, void* out, float* lse, int64_t n_
   }
   STG_REQUIRE(dtype == STGCMA_BF16, "mha_fwd: bad dtype %d", dtype);
   STG_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "mha_fwd: operands must be 16-byte aligned");
+  if (inner > 1 && seq_len <= 16 && n_seq / inner < (1 << 30)) {
+    // temporal attention: an HBM stream with a 16 x 16 score tile per (token, head) -- the tile kernels of temporal_tc.cu
+    rc = temporal_mha_fwd_bf16(qkv, out, lse, (int)(n_seq / inner), seq_len, inner, heads, hd, st);
+    if (rc != -1) return rc;
+  }
   MHA_DISPATCH(hd, fwd_bf16, qkv, out, lse, sq, heads, st);
 }
 
@@ -697,5 +711,9 @@ extern "C" int stgcma_mha_bwd(const void* qkv, const void* out, const float* lse
   STG_REQUIRE(work, "mha_bwd(bf16): needs the [rows, heads] fp32 work buffer");
   STG_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
               "mha_bwd: operands must be 16-byte aligned");
+  if (inner > 1 && seq_len <= 16 && n_seq / inner < (1 << 30)) {
+    rc = temporal_mha_bwd_bf16(qkv, dout, dqkv, (int)(n_seq / inner), seq_len, inner, heads, hd, st);
+    if (rc != -1) return rc;
+  }
   MHA_DISPATCH(hd, bwd_bf16, qkv, out, lse, dout, dqkv, work, sq, heads, st);
 }
