@@ -221,10 +221,10 @@ __global__ void __launch_bounds__(256) ln_bwd_rr_kernel(const TD* __restrict__ d
   const float mean = ok ? mean_in[row] : 0.f, rstd = ok ? rstd_in[row] : 0.f;
   const TD* dyrow = dy + (ok ? row : 0) * (int64_t)C;
   float gg[VMAX][4], xh[VMAX][4];
-  // Short rows (VMAX = 4): the residual gradient is loaded together with dy / x, before the row reduction, so that a
+  // Rows up to 1024 channels (VMAX <= 8): the residual gradient is loaded together with dy / x, before the row reduction, so that a
   // row has ONE exposed memory round trip instead of two (every load of the row is in flight at once).  dres may alias
   // dx: this lane still reads its own elements before it writes them.
-  constexpr bool EARLY = VMAX <= 4;
+  constexpr bool EARLY = VMAX <= 8;
   float rr[EARLY ? VMAX : 1][4];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -284,8 +284,8 @@ static bool rr_config(int C, int& lpr, int& vpl, int& vmax) {
   if (per4 % lpr) return false;
   vpl = per4 / lpr;
   if (vpl > 12) return false;
-  vmax = (vpl <= 4) ? 4 : 12;
-  if (vmax == 12 && lpr != 32) return false;
+  vmax = (vpl <= 4) ? 4 : (vpl <= 8 ? 8 : 12);    // 8: C = 544 .. 1024 (CLIP ViT-B/16 D = 768, Swin-T stage 3)
+  if (vmax > 4 && lpr != 32) return false;
   return true;
 }
 
@@ -303,6 +303,7 @@ static bool ln_fwd_rr_dispatch(const void* x, const float* gamma, const float* b
   int lpr, vpl, vmax;
   if (!rr_config(C, lpr, vpl, vmax)) return false;
   if (vmax == 12) ln_fwd_rr_launch<TX, TY, MERGE, 32, 12>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
+  else if (vmax == 8) ln_fwd_rr_launch<TX, TY, MERGE, 32, 8>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
   else if (lpr == 8) ln_fwd_rr_launch<TX, TY, MERGE, 8, 4>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
   else if (lpr == 16) ln_fwd_rr_launch<TX, TY, MERGE, 16, 4>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
   else ln_fwd_rr_launch<TX, TY, MERGE, 32, 4>(x, gamma, beta, y, mean, rstd, rows, C, R, vpl, st);
@@ -338,6 +339,7 @@ static bool ln_bwd_rr_dispatch(const void* dy, const void* x, const float* mean,
   int lpr, vpl, vmax;
   if (!rr_config(C, lpr, vpl, vmax)) return false;
   if (vmax == 12) ln_bwd_rr_launch<TD, TX, TC, MERGE, 32, 12>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
+  else if (vmax == 8) ln_bwd_rr_launch<TD, TX, TC, MERGE, 32, 8>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
   else if (lpr == 8) ln_bwd_rr_launch<TD, TX, TC, MERGE, 8, 4>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
   else if (lpr == 16) ln_bwd_rr_launch<TD, TX, TC, MERGE, 16, 4>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);
   else ln_bwd_rr_launch<TD, TX, TC, MERGE, 32, 4>(dy, x, mean, rstd, gamma, dres, dx, dx_copy, rows, C, R, vpl, st);

@@ -14,6 +14,7 @@
 //     dq  : query-tile owner.   D_i = <dO_i, O_i>; P = exp(s - lse_i); dS = P (dO_i.v_j - D_i); dQ_i = scale * dS K
 //     dkv : key-tile owner.     P^T and dS^T recomputed from (k_i, q_j), (v_i, dO_j): dV_i = P^T dO, dK_i = scale * dS^T Q
 // fp32 check mode: one thread per row, everything from global memory (numerics reference, not a fast path).
+#include <stdlib.h>
 #include <mutex>
 #include "mma.cuh"
 
@@ -656,6 +657,8 @@ static int check_args(const char* what, int64_t n_seq, int seq_len, int inner, i
 // temporal_tc.cu: whole-sequence-in-one-tile kernels for T <= 16 frames of a [clips, T, tokens] layout (-1: not covered)
 int temporal_mha_fwd_bf16(const void* qkv, void* out, float* lse, int B, int T, int L, int heads, int hd, cudaStream_t st);
 int temporal_mha_bwd_bf16(const void* qkv, const void* dout, void* dqkv, int B, int T, int L, int heads, int hd, cudaStream_t st);
+// mha_tc.cu: tcgen05 / TMEM kernels for contiguous sequences of 65 .. 208 tokens (-1: not covered)
+int mha_tc_fwd_bf16(const void* qkv, void* out, float* lse, int64_t n_seq, int seq_len, int heads, int hd, cudaStream_t st);
 }  // namespace stgcma
 
 using namespace stgcma;
@@ -689,6 +692,10 @@ extern "C" int stgcma_mha_fwd(const void* qkv, void* out, float* lse, int64_t n_
   if (inner > 1 && seq_len <= 16 && n_seq / inner < (1 << 30)) {
     // temporal attention: an HBM stream with a 16 x 16 score tile per (token, head) -- the tile kernels of temporal_tc.cu
     rc = temporal_mha_fwd_bf16(qkv, out, lse, (int)(n_seq / inner), seq_len, inner, heads, hd, st);
+    if (rc != -1) return rc;
+  }
+  if (inner == 1 && !getenv("STGCMA_MHA_NO_TC")) {
+    rc = mha_tc_fwd_bf16(qkv, out, lse, n_seq, seq_len, heads, hd, st);
     if (rc != -1) return rc;
   }
   MHA_DISPATCH(hd, fwd_bf16, qkv, out, lse, sq, heads, st);
