@@ -659,6 +659,8 @@ int temporal_mha_fwd_bf16(const void* qkv, void* out, float* lse, int B, int T, 
 int temporal_mha_bwd_bf16(const void* qkv, const void* dout, void* dqkv, int B, int T, int L, int heads, int hd, cudaStream_t st);
 // mha_tc.cu: tcgen05 / TMEM kernels for contiguous sequences of 65 .. 208 tokens (-1: not covered)
 int mha_tc_fwd_bf16(const void* qkv, void* out, float* lse, int64_t n_seq, int seq_len, int heads, int hd, cudaStream_t st);
+int mha_tc_bwd_bf16(const void* qkv, const void* o, const float* lse, const void* dout, void* dqkv, int64_t n_seq, int seq_len,
+                    int heads, int hd, cudaStream_t st);
 }  // namespace stgcma
 
 using namespace stgcma;
@@ -720,6 +722,10 @@ extern "C" int stgcma_mha_bwd(const void* qkv, const void* out, const float* lse
               "mha_bwd: operands must be 16-byte aligned");
   if (inner > 1 && seq_len <= 16 && n_seq / inner < (1 << 30)) {
     rc = temporal_mha_bwd_bf16(qkv, dout, dqkv, (int)(n_seq / inner), seq_len, inner, heads, hd, st);
+    if (rc != -1) return rc;
+  }
+  if (inner == 1 && !getenv("STGCMA_MHA_NO_TC")) {
+    rc = mha_tc_bwd_bf16(qkv, out, lse, dout, dqkv, n_seq, seq_len, heads, hd, st);
     if (rc != -1) return rc;
   }
   MHA_DISPATCH(hd, bwd_bf16, qkv, out, lse, dout, dqkv, work, sq, heads, st);

@@ -85,8 +85,8 @@ def _step(m, a, v, labels, mode, is_trainable):
 def test_dropin_vs_unmodified_reference_module_on_gpu(family, dtype):
     Omod, Cfg, kw, make_ref, make_ours = FAMILIES[family]
     cfg = Cfg(**kw)
-    sd = Omod.make_state(cfg, seed=11, bf16_exact=True)
-    a, v, labels = Omod.make_inputs(cfg, 2, seed=11)
+    sd = Omod.make_state(cfg, seed=3, bf16_exact=True)
+    a, v, labels = Omod.make_inputs(cfg, 2, seed=3)
     ref = make_ref(kw, "fusion").double().cuda()
     if family == "clip":      # the reference's LayerNorm casts its input to fp32 (CLIP_AVE.py:38): its parameters must be fp32
         refmod = shim.load_reference("AVE/model/CLIP_AVE.py", "_ref_CLIP_AVE")
