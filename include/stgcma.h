@@ -22,7 +22,7 @@
  *     use the activation dtype.
  *   - activations are token-major [rows, channels]; "rows" of the two modalities are stacked
  *     video first, audio second, because both streams share the frozen weights.
- *   - refuses to run (STGCMA_EARCH) on anything that is not compute capability 10.x.
+ *   - refuses to run (STGCMA_EARCH) on anything that is not compute capability 10.0 (the cubins are sm_100a).
  */
 #ifndef STGCMA_H_
 #define STGCMA_H_
@@ -54,7 +54,7 @@ enum {
 
 const char* stgcma_last_error(void);
 int stgcma_version(void);
-/* 0 when device `dev` can run the library (compute capability 10.x), STGCMA_EARCH otherwise */
+/* 0 when device `dev` can run the library (compute capability 10.0), STGCMA_EARCH otherwise */
 int stgcma_check_device(int dev);
 
 /* ---- PatchEmbed3D: Conv3d(k=s=(1,4,4)) + bias + LayerNorm   (Swin_AVE.py:1104-1124) -------

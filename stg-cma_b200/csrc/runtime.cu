@@ -48,7 +48,7 @@ extern "C" int stgcma_check_device(int dev) {
     stgcma::set_error("check_device: %s", cudaGetErrorString(e));
     return STGCMA_ECUDA;
   }
-  if (p.major != 10) {
+  if (p.major != 10 || p.minor != 0) {   // the cubins are sm_100a: arch-specific, not forward compatible to other 10.x parts
     stgcma::set_error("check_device: device %d is sm_%d%d; libstgcma is built for sm_100a only (no fallback)", dev,
                       p.major, p.minor);
     return STGCMA_EARCH;

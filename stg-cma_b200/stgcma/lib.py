@@ -165,7 +165,14 @@ def require_device(*tensors):
         if not t.is_cuda:
             raise StgcmaError("STG-CMA B200 path needs CUDA tensors: there is no CPU fallback")
     dev = tensors[0].device
-    check_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if any(t.device != dev for t in tensors):
+        raise StgcmaError("STG-CMA B200 path: all inputs must live on the same device")
+    if idx != torch.cuda.current_device():
+        # kernels are enqueued on torch's CURRENT stream; pointers of another device would be launched in the wrong context
+        raise StgcmaError(f"inputs are on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}: "
+                          "call torch.cuda.set_device() (one process per GPU) before the step")
+    check_device(idx)
 
 
 # ---------------------------------------------------------------------------------------------

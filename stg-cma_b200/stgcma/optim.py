@@ -64,10 +64,16 @@ class FusedAdam(torch.optim.Optimizer):
                 if gr.dtype != torch.float32 or not gr.is_contiguous() or gr.is_sparse:
                     raise L_.StgcmaError("FusedAdam: gradients must be dense contiguous fp32 tensors")
                 st = self.state[p]
-                st["step"] += 1
+                # a torch.optim.Adam checkpoint stores `step` as a tensor: coerce, so equal counts share a slot
+                st["step"] = int(st["step"]) + 1
+                m, v = st["exp_avg"], st["exp_avg_sq"]
+                if m.dtype != torch.float32 or v.dtype != torch.float32 or not m.is_contiguous() or not v.is_contiguous() \
+                        or m.device != p.device or v.device != p.device:
+                    raise L_.StgcmaError("FusedAdam: exp_avg / exp_avg_sq must be contiguous fp32 tensors on the parameter's device")
                 slot = slots.setdefault((gi, st["step"]), len(slots))
                 active.append((slot, p, gr))
-                key.append((p.data_ptr(), gr.data_ptr(), slot))
+                # the moment buffers are part of the key: load_state_dict() replaces them
+                key.append((p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), slot))
         if not active:
             return loss
         if len(slots) > L_.ADAM_MAX_GROUPS:

@@ -29,6 +29,44 @@ def test_library_exports_every_declared_symbol():
     assert h.stgcma_version() >= 100
 
 
+def declared_prototypes():
+    """{name: [ctypes type per parameter]} parsed from the C prototypes of include/stgcma.h."""
+    src = open(os.path.join(ROOT, "include", "stgcma.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|const char\*)\s+(stgcma_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        types = []
+        for a in (x.strip() for x in args.split(",")):
+            if a in ("void", ""):
+                continue
+            if "*" in a:
+                types.append(ctypes.c_void_p)
+            elif a.startswith("int64_t"):
+                types.append(ctypes.c_int64)
+            elif a.startswith("float"):
+                types.append(ctypes.c_float)
+            elif a.startswith("int"):
+                types.append(ctypes.c_int)
+            else:
+                raise AssertionError(f"unparsed parameter {a!r} of {name}")
+        protos[name] = types
+    return protos
+
+
+def test_ctypes_signatures_match_the_header():
+    """stgcma.lib._SIGNATURES (the argtypes every call goes through) against the
+    prototypes of include/stgcma.h, parameter by parameter."""
+    import stgcma.lib as lib
+    protos = declared_prototypes()
+    assert set(lib._SIGNATURES) <= set(protos)
+    for name, argtypes in lib._SIGNATURES.items():
+        want = protos[name]
+        got = list(argtypes)
+        assert len(got) == len(want), (name, len(got), len(want))
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert g is w, f"{name}: parameter {i} is {g.__name__} in lib.py, {w.__name__} in stgcma.h"
+
+
 def test_pack_entry_matches_struct_layout():
     import stgcma.lib as lib
     assert lib.PACK_ENTRY.size == 48  # sizeof(StgcmaPackEntry): 2 pointers, 2 int32, 2 int64, 2 int32

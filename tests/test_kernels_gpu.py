@@ -545,3 +545,37 @@ def test_fused_adam_matches_torch_adam():
     sd = ours.state_dict()
     assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     assert rel(ours.state[our_p[0]]["exp_avg_sq"], ref.state[ref_p[0]]["exp_avg_sq"]) < 1e-6
+
+
+def test_fused_adam_load_state_dict_after_step():
+    """load_state_dict() on a FusedAdam that has already stepped replaces the moment tensors (and a
+    torch.optim.Adam checkpoint stores `step` as a tensor): the device table must follow, and the next step must equal
+    torch.optim.Adam's."""
+    from stgcma.optim import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    shapes = [(48, 768), (768,), (1,), (29, 512)]
+    base = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(3)]
+    pa = [torch.nn.Parameter(t.clone().cuda()) for t in base]
+    pb = [torch.nn.Parameter(t.clone().cuda()) for t in base]
+    kw = dict(weight_decay=5e-7, betas=(0.95, 0.999))
+    A = FusedAdam([{"params": pa[:2], "lr": 1e-3}, {"params": pa[2:], "lr": 1e-2}], **kw)
+    B = torch.optim.Adam([{"params": pb[:2], "lr": 1e-3}, {"params": pb[2:], "lr": 1e-2}], **kw)
+
+    def set_grads(ps, k):
+        for p, gr in zip(ps, grads[k]):
+            p.grad = gr.clone().cuda()
+
+    set_grads(pa, 0); A.step()                    # A has stepped: its device table exists
+    for k in (0, 1):
+        set_grads(pb, k); B.step()
+    import copy
+    A.load_state_dict(copy.deepcopy(B.state_dict()))   # moments + tensor-valued steps (load_state_dict does not copy tensors)
+    with torch.no_grad():
+        for p, q in zip(pa, pb):
+            p.copy_(q)
+    set_grads(pa, 2); set_grads(pb, 2)
+    A.step(); B.step()
+    torch.cuda.synchronize()
+    for p, q in zip(pa, pb):
+        assert rel(p.detach(), q.detach()) < 1e-6

@@ -280,3 +280,23 @@ def test_micro_batch_lanes_match_single_chain():
     assert torch.equal(out1, out2)
     for n in g1:
         assert rel(g2[n], g1[n]) < 2e-3, n
+
+
+def test_side_stream_dw_matches_main_stream():
+    """The adapters' weight-gradient kernels run on a side stream, off the dX critical path (engine.backward); the main
+    chain must never rewrite a buffer they still read.  A stage of depth 4 exercises the block -> block hand-over after a
+    temporal sub-block (the buffer rotation dD -> dE -> dB of engine._backward_part): gradients with and without the side
+    stream agree up to the order of the fp32 atomics."""
+    kw = dict(img_size=112, num_frames=3, embed_dim=32, depths=[4, 2], num_heads=[1, 2], adapter_mlp_ratio=[0.25, 0.25], label_dim=7)
+    cfg = O.SwinAVEConfig(**kw)
+    sd = O.make_state(cfg, seed=17)
+    a, v, labels = O.make_inputs(cfg, 4, seed=17)
+    m = build(kw, "fusion", torch.bfloat16, sd)
+    runs = []
+    for side in (False, True, True, True):        # repeated: a race is timing dependent
+        m.engine().side_stream_dw = side
+        _, _, g = step(m, a, v, labels, "fusion")
+        runs.append(g)
+    for g in runs[1:]:
+        for n in runs[0]:
+            assert rel(g[n], runs[0][n]) < 1e-5, n
