@@ -380,9 +380,17 @@ static int bwd_launch(const void* h, const void* hpre, const float* gate, const 
 
 }  // namespace xtc
 
+// xmodal_tc5.cu: tcgen05 / TMEM kernel for long rows (-1: shape not covered)
+int xmodal_global_fwd_tc5(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L, int La,
+                          int rp, cudaStream_t st);
+
 // entry points used by xmodal.cu's bf16 dispatch; return -1 for an unsupported rp
 int xmodal_global_fwd_bf16(const void* h, const float* gate, void* out, void* attn_out, float* lse, int64_t frames, int L,
                            int La, int rp, cudaStream_t st) {
+  {
+    const int rc = xmodal_global_fwd_tc5(h, gate, out, attn_out, lse, frames, L, La, rp, st);
+    if (rc != -1) return rc;
+  }
   // 4 warps (64 own rows) per CTA: measured against 8 and 2 warps at L = 3136 (32 clips): 5.1 / 5.7 / 5.5 ms forward,
   // 10.4 / 11.1 / 11.2 ms backward per step -- two block-wide barriers per 64-row tile are cheaper with fewer warps, and
   // the streamed tiles are L2 hits whichever CTA re-reads them
