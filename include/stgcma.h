@@ -49,7 +49,12 @@ enum {
   STGCMA_EPI_DGELU = 2,   /* out = v * gelu_erf'(aux[m,n])   (backward through nn.GELU)      */
   STGCMA_EPI_MULAUX = 3,  /* out = v * aux[m,n]              (dropout keep-mask)             */
   STGCMA_EPI_QGELU = 4,   /* out = v * sigmoid(1.702 v) (CLIP's QuickGELU, CLIP_AVE.py:41-43); out_pre = v   */
-  STGCMA_EPI_DQGELU = 5   /* out = v * d/dx[x sigmoid(1.702 x)](aux[m,n])                          */
+  STGCMA_EPI_DQGELU = 5,  /* out = v * d/dx[x sigmoid(1.702 x)](aux[m,n])                          */
+  /* derivative-saving forms: the forward evaluates the activation AND its derivative (the erf / sigmoid terms are
+   * shared) and stores the DERIVATIVE in out_pre; the backward of the layer is then the cheap MULAUX epilogue
+   * (out = v * aux) instead of a second transcendental evaluation per element.                                  */
+  STGCMA_EPI_GELU_G = 6,  /* out = gelu_erf(v);          out_pre = gelu_erf'(v)                                   */
+  STGCMA_EPI_QGELU_G = 7  /* out = v * sigmoid(1.702 v); out_pre = d/dv [v sigmoid(1.702 v)]                      */
 };
 
 const char* stgcma_last_error(void);

@@ -134,6 +134,19 @@ __device__ __forceinline__ float qgelu_grad(float x) {
   const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * x));
   return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
 }
+// activation and derivative from ONE evaluation of the shared transcendental terms
+__device__ __forceinline__ void gelu_val_grad_fast(float x, float& y, float& dy) {
+  float e, g;
+  erf_exp_fast(x, e, g);
+  const float cdf = 0.5f * (1.0f + e);
+  y = x * cdf;
+  dy = fmaf(x * 0.39894228040143268f, g, cdf);
+}
+__device__ __forceinline__ void qgelu_val_grad(float x, float& y, float& dy) {
+  const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * x));
+  y = x * s;
+  dy = s * fmaf(1.702f * x, 1.0f - s, 1.0f);
+}
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float e, g;
   erf_exp_fast(x, e, g);

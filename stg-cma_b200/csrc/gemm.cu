@@ -44,6 +44,14 @@ __device__ __forceinline__ void epi_elem(const EpiParams& p, int64_t row, int co
       const float a = ld_f(reinterpret_cast<const T*>(p.aux) + off);
       st_f(out + off, v * qgelu_grad(a));
     } break;
+    case STGCMA_EPI_GELU_G: {
+      if (p.out_pre) st_f(reinterpret_cast<T*>(p.out_pre) + off, gelu_erf_grad(v));
+      st_f(out + off, gelu_erf(v));
+    } break;
+    case STGCMA_EPI_QGELU_G: {
+      if (p.out_pre) st_f(reinterpret_cast<T*>(p.out_pre) + off, qgelu_grad(v));
+      st_f(out + off, qgelu(v));
+    } break;
     default: {
       const float a = ld_f(reinterpret_cast<const T*>(p.aux) + off);
       st_f(out + off, v * a);
@@ -89,7 +97,7 @@ __device__ __forceinline__ void epi_load(const EpiParams& p, int64_t off0, int64
         }
       }
       if (NRES >= 2) r.b[ps] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res2) + off);
-    } else if (MODE != STGCMA_EPI_GELU && MODE != STGCMA_EPI_QGELU) {
+    } else if (MODE != STGCMA_EPI_GELU && MODE != STGCMA_EPI_QGELU && MODE != STGCMA_EPI_GELU_G && MODE != STGCMA_EPI_QGELU_G) {
       r.a[ps][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + off);
     }
   }
@@ -124,6 +132,14 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int64_t off, int p
     if (p.out_pre) store8(reinterpret_cast<bf16*>(p.out_pre) + off, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (MODE == STGCMA_EPI_GELU) ? gelu_fast(v[i]) : qgelu(v[i]);
+  } else if (MODE == STGCMA_EPI_GELU_G || MODE == STGCMA_EPI_QGELU_G) {
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE == STGCMA_EPI_GELU_G) gelu_val_grad_fast(v[i], v[i], d[i]);
+      else qgelu_val_grad(v[i], v[i], d[i]);
+    }
+    if (p.out_pre) store8(reinterpret_cast<bf16*>(p.out_pre) + off, d);
   } else {
     float t[8];
     unpack8(r.a[ps][0], t);
@@ -474,7 +490,7 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   // matter more than the deeper ring).  Measured per shape with scripts/gemm_shapes.py (profiles/r01f): qkv stage 2
   // 775 -> 859 TFLOP/s, qkv stage 3 908 -> 1176, proj stage 3 780 -> 961; mlp.fc1 + GELU stage 2 532 -> 509 (kept at 2).
   const bool act_epi = ep.mode == STGCMA_EPI_GELU || ep.mode == STGCMA_EPI_DGELU || ep.mode == STGCMA_EPI_QGELU ||
-                       ep.mode == STGCMA_EPI_DQGELU;
+                       ep.mode == STGCMA_EPI_DQGELU || ep.mode == STGCMA_EPI_GELU_G || ep.mode == STGCMA_EPI_QGELU_G;
   const int occ = (K >= 1024 || (K >= 256 && N >= 384 && (!act_epi || K >= 768))) ? 1 : 2;
   const int bn_max = occ == 1 ? 256 : 128;
   int best_bn = 16;
@@ -572,6 +588,12 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
     case STGCMA_EPI_DQGELU:
       STG_REQUIRE(!f32, "gemm(bf16): QuickGELU epilogues write the activation dtype");
       STG_TC_LAUNCH(STGCMA_EPI_DQGELU, false, 0);
+    case STGCMA_EPI_GELU_G:
+      STG_REQUIRE(!f32, "gemm(bf16): derivative-saving epilogues write the activation dtype");
+      STG_TC_LAUNCH(STGCMA_EPI_GELU_G, false, 0);
+    case STGCMA_EPI_QGELU_G:
+      STG_REQUIRE(!f32, "gemm(bf16): derivative-saving epilogues write the activation dtype");
+      STG_TC_LAUNCH(STGCMA_EPI_QGELU_G, false, 0);
     default:
       if (f32) STG_TC_LAUNCH(STGCMA_EPI_MULAUX, true, 0);
       STG_TC_LAUNCH(STGCMA_EPI_MULAUX, false, 0);
@@ -688,7 +710,7 @@ extern "C" int stgcma_gemm(const void* A, const void* W, const float* bias, cons
   STG_REQUIRE(out_dtype == dtype || out_dtype == STGCMA_F32, "gemm: out_dtype must be the activation dtype or fp32");
   STG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
   STG_REQUIRE(groups >= 1 && M % groups == 0, "gemm: M=%lld not divisible by groups=%d", (long long)M, groups);
-  STG_REQUIRE(epilogue >= STGCMA_EPI_LINEAR && epilogue <= STGCMA_EPI_DQGELU, "gemm: bad epilogue %d", epilogue);
+  STG_REQUIRE(epilogue >= STGCMA_EPI_LINEAR && epilogue <= STGCMA_EPI_QGELU_G, "gemm: bad epilogue %d", epilogue);
   STG_REQUIRE((epilogue != STGCMA_EPI_DGELU && epilogue != STGCMA_EPI_MULAUX && epilogue != STGCMA_EPI_DQGELU) || aux,
               "gemm: epilogue %d needs aux", epilogue);
   STG_REQUIRE(A && W && out, "gemm: null operand");

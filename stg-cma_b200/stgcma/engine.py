@@ -426,7 +426,8 @@ class SwinAVEEngine:
                     xn = buf(f"xn{s}", M, C)
                     L_.layernorm_fwd(x, f["n2g"], f["n2b"], xn, mean, rstd, M, C)
                     fpre, fact = buf(k + "fpre", M, hid), buf(f"fact{s}", M, hid)
-                    L_.gemm(xn, f["fc1_w"], fact, M, hid, C, bias=f["fc1_b"], out_pre=fpre, epi=L_.EPI_GELU)
+                    # fpre holds GELU'(fc1(xn)) (derivative-saving epilogue): the backward of the activation is a multiply
+                    L_.gemm(xn, f["fc1_w"], fact, M, hid, C, bias=f["fc1_b"], out_pre=fpre, epi=L_.EPI_GELU_G)
                     L_.gemm(fact, f["fc2_w"], y, M, C, hid, bias=f["fc2_b"])
                     L_.gemm(y, A["w1"], h, M, rp, C, bias=A["b1"], out_pre=hpre, groups=2, epi=L_.EPI_GELU)
                 if fusion:
@@ -655,7 +656,7 @@ class SwinAVEEngine:
                     dy = buf(f"dA{s}", M, C)
                     L_.gemm(dhpre, A["w1t"], dy, M, C, rp, res1=dxb, groups=2)
                     dfpre = buf(f"dfpre{s}", M, hid)
-                    L_.gemm(dy, f["fc2_wt"], dfpre, M, hid, C, aux=slot(k + "fpre"), epi=L_.EPI_DGELU)
+                    L_.gemm(dy, f["fc2_wt"], dfpre, M, hid, C, aux=slot(k + "fpre"), epi=L_.EPI_MULAUX)
                     L_.gemm(dfpre, f["fc1_wt"], dxn, M, C, hid)
                 # the three sub-blocks rotate over three buffer pairs (G -> dE, S -> dB, T -> dD): the side-stream dW kernels
                 # launched above still read dxb, which after a (T) sub-block IS dDb -- writing this sub-block's result there

@@ -11,7 +11,7 @@ import struct
 import torch
 
 F32, BF16 = 0, 1
-EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX, EPI_QGELU, EPI_DQGELU = 0, 1, 2, 3, 4, 5
+EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX, EPI_QGELU, EPI_DQGELU, EPI_GELU_G, EPI_QGELU_G = 0, 1, 2, 3, 4, 5, 6, 7
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstgcma.so")

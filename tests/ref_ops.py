@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from oracle import swin_ave_oracle as O
 
-EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX, EPI_QGELU, EPI_DQGELU = 0, 1, 2, 3, 4, 5
+EPI_LINEAR, EPI_GELU, EPI_DGELU, EPI_MULAUX, EPI_QGELU, EPI_DQGELU, EPI_GELU_G, EPI_QGELU_G = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def _view2d(t, rows, cols, ld):
@@ -128,6 +128,15 @@ def gemm(A, W, out, M, N, K, *, bias=None, res1=None, res2=None, rowscale=None, 
         a = _c(_view2d(aux, M, N, ldo))
         sg = torch.sigmoid(1.702 * a)
         o.copy_(v * sg * (1.0 + 1.702 * a * (1.0 - sg)))
+    elif epi == EPI_GELU_G:       # derivative-saving forms: out_pre receives the activation's derivative
+        if out_pre is not None:
+            _view2d(out_pre, M, N, ldo).copy_(_dgelu(v))
+        o.copy_(_gelu(v))
+    elif epi == EPI_QGELU_G:
+        sg = torch.sigmoid(1.702 * v)
+        if out_pre is not None:
+            _view2d(out_pre, M, N, ldo).copy_(sg * (1.0 + 1.702 * v * (1.0 - sg)))
+        o.copy_(v * sg)
     else:
         o.copy_(v * _c(_view2d(aux, M, N, ldo)))
 

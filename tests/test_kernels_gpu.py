@@ -55,6 +55,9 @@ GEMM_CASES = [
     (394, 3072, 768, 1, R.EPI_QGELU, dict(bias=True, out_pre=True)),
     (394, 768, 3072, 1, R.EPI_DQGELU, dict(aux=True)),
     (200, 256, 64, 1, R.EPI_QGELU, dict(bias=True)),
+    # derivative-saving forms: out_pre = activation'(v)
+    (394, 3072, 768, 1, R.EPI_QGELU_G, dict(bias=True, out_pre=True)),
+    (384, 1536, 384, 1, R.EPI_GELU_G, dict(bias=True, out_pre=True)),
     # skinny-K residual GEMMs (gemm_skinny.cu): adapter D_fc2 + residual adds into the fp32 stream, and the dX of D_fc1
     (2 * 147, 96, 16, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, f32=True)),     # ragged 16-row slabs per group
     (2 * 1000, 384, 32, 2, R.EPI_LINEAR, dict(bias=True, res1=True, res2=True, f32=True)),
