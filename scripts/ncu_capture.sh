@@ -8,6 +8,6 @@ for spec in "$@"; do
   IFS=@ read -r tag rx skip <<< "$spec"
   timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
       --kernel-name-base demangled -k "regex:$rx" -s "${skip:-0}" -c 1 -f -o "gpurun_out/ncu_$tag" \
-      python scripts/profile_step.py --batch "${PROFILE_BATCH:-4}" > "gpurun_out/ncu_$tag.log" 2>&1
+      python scripts/profile_step.py --model "${PROFILE_MODEL:-swin_t}" --batch "${PROFILE_BATCH:-4}" > "gpurun_out/ncu_$tag.log" 2>&1
   echo "ncu $tag exit $?"
 done

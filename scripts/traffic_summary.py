@@ -25,10 +25,15 @@ CLASS = [  # kernel-name regex -> C-ABI entry point (the key bench.py's live pro
     (r"xw_bwd_kernel", "stgcma_xmodal_window_bwd"), (r"xw_fwd_kernel", "stgcma_xmodal_window_fwd"),
     (r"patch_embed", "stgcma_patch_embed_fwd"), (r"pack_params", "stgcma_pack_params"),
     (r"head_pool_bwd", "stgcma_head_pool_bwd"), (r"head_pool_fwd", "stgcma_head_pool_fwd"),
+    # CLIP-ViT variant: the temporal MHA runs the tt_* tile kernels (classified above as temporal_attn when the Swin
+    # model runs; `main` re-labels them for a clip workload)
+    (r"mha_tc_bwd|mha_bwd_dq|mha_bwd_dkv|mha_bwd_simt", "stgcma_mha_bwd"), (r"mha_tc_fwd|mha_fwd_kernel|mha_fwd_simt", "stgcma_mha_fwd"),
+    (r"im2col", "stgcma_im2col"), (r"clip_embed", "stgcma_clip_embed_fwd"), (r"clip_temb", "stgcma_clip_temb_bwd"),
+    (r"cls_ln_bwd", "stgcma_cls_ln_bwd"), (r"cls_ln_fwd", "stgcma_cls_ln_fwd"), (r"adam_kernel", "stgcma_adam_step"),
 ]
 
 
-def main(path, batch):
+def main(path, batch, workload="swin_t"):
     with open(path) as f:
         lines = [l for l in f if l.startswith('"')]
     rd = csv.reader(lines)
@@ -49,6 +54,8 @@ def main(path, batch):
     out = {}
     for d in per.values():
         cls = next((c for rx, c in CLASS if re.search(rx, d["name"])), "other")
+        if workload.startswith("clip") and cls.startswith("stgcma_temporal_attn"):
+            cls = cls.replace("temporal_attn", "mha")
         o = out.setdefault(cls, dict(launches=0, dram_bytes=0.0, ms=0.0))
         o["launches"] += 1
         o["dram_bytes"] += d["bytes"]
@@ -57,11 +64,11 @@ def main(path, batch):
         o["dram_bytes_per_launch"] = round(o["dram_bytes"] / o["launches"])
         o["dram_bytes"] = round(o["dram_bytes"])
         o["ms"] = round(o["ms"], 3)
-    print(json.dumps({"workload": "swin_t fusion train step", "clips_per_gpu": batch,
+    print(json.dumps({"workload": f"{workload} fusion train step", "clips_per_gpu": batch,
                       "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, one profiled step "
                                 "(--clock-control none; launches serialised, caches cold between replays)",
                       "classes": dict(sorted(out.items(), key=lambda kv: -kv[1]["ms"]))}, indent=1))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]))
+    main(sys.argv[1], int(sys.argv[2]), *(sys.argv[3:4]))
