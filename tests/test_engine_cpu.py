@@ -138,3 +138,53 @@ def test_refuses_unfrozen_backbone_and_cpu(monkeypatch):
         m(a, v, "fusion")
     with pytest.raises(NotImplementedError):
         build(TINY, "videoonly", torch.float32)
+
+
+def test_pretrained_checkpoint_route_matches_reference(tmp_path, capsys):
+    """`pretrained=<path>` (the route every real run takes, run_adapt_ave29.py:156-165): a synthetic ImageNet-style Swin
+    checkpoint -- 2-D patch conv, no audio stream, no adapters, one unexpected key -- loaded by the drop-in and by the
+    UNMODIFIED reference (Swin_AVE.py:1363-1413) must give identical state dicts: conv inflation over time, audio conv =
+    RGB mean, audio patch-norm copied, adapter D_fc2 / gates zero afterwards, same Missing / Unexpected key report."""
+    from oracle import shim
+    if not shim.reference_available():
+        pytest.skip("the unmodified reference is neither at /root/reference nor staged in oracle/_ref")
+    ref = shim.load_reference()
+    kw = dict(label_dim=7, patch_size=[1, 4, 4], num_frames=3, embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=7,
+              ftmode="fusion", adapter_mlp_ratio=[0.25, 0.25], img_size=112)
+    torch.manual_seed(0)
+    donor = ref.SwinTransformer2D_Adapter_New(pretrained=None, **kw)
+    g = torch.Generator().manual_seed(1)
+    ck = {}
+    for k, t in donor.state_dict().items():
+        if any(s in k for s in ("Adapter", "gate_", "temporal_position", "t_relative", "_audio", "mlp_head")):
+            continue   # an ImageNet Swin checkpoint has none of these
+        ck[k] = torch.randn(t.shape, generator=g) * 0.05 if t.is_floating_point() and "attn_mask" not in k else t.clone()
+    ck["patch_embed.proj.weight"] = torch.randn(32, 3, 4, 4, generator=g) * 0.05   # 2-D conv, inflated by the loader
+    ck["head.weight"] = torch.randn(5, 64, generator=g)                            # unexpected key: reported, ignored
+    path = str(tmp_path / "swin_synth.pth")
+    torch.save({"model": ck}, path)
+
+    torch.manual_seed(2)
+    r = ref.SwinTransformer2D_Adapter_New(pretrained=path, **kw)
+    ref_log = capsys.readouterr().out
+    import model
+    torch.manual_seed(2)
+    m = model.Swin_AVE.SwinTransformer2D_Adapter_New(pretrained=path, **kw)
+    our_log = capsys.readouterr().out
+    rs, ms = r.state_dict(), m.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    loaded = set(ck) | {"patch_embed_audio.proj.weight", "patch_embed_audio.proj.bias", "patch_embed_audio.norm.weight", "patch_embed_audio.norm.bias"}
+    for k in rs:
+        if k in loaded or "D_fc2" in k or "gate_" in k or not rs[k].is_floating_point():
+            assert torch.equal(rs[k], ms[k]), k   # checkpoint-derived tensors and the zero-initialised ones: bit equal
+        else:
+            assert rs[k].shape == ms[k].shape, k  # randomly initialised (trunc-normal draws differ in order)
+    assert ms["patch_embed.proj.weight"].shape == (32, 3, 1, 4, 4) and ms["patch_embed_audio.proj.weight"].shape == (32, 1, 1, 4, 4)
+    assert torch.equal(ms["patch_embed_audio.proj.weight"], ms["patch_embed.proj.weight"].mean(dim=1, keepdim=True))
+
+    def report(log, tag):
+        line = next(l for l in log.splitlines() if l.startswith(tag))
+        return sorted(eval(line[len(tag):]))
+    for tag in ("Missing keys: ", "Unexpected keys: "):
+        assert report(ref_log, tag) == report(our_log, tag), tag
+    assert report(our_log, "Unexpected keys: ") == ["head.weight"]
