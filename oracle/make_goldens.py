@@ -12,6 +12,7 @@ the full-width Swin-T case the small tensors in full and an L2 norm + 64-sample 
 every tensor, to keep the fixture small).
 """
 import os
+import sys
 
 import torch
 
@@ -31,7 +32,10 @@ def probe_index(numel, n=64):
 def main():
     assert shim.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])   # optional: regenerate only the named cases
     for name, kw, batch, mode in CASES:
+        if only and name not in only:
+            continue
         cfg = O.SwinAVEConfig(**kw)
         sd = O.make_state(cfg, seed=SEED, dtype=torch.float64, **STATE_KW)
         a, v, labels = O.make_inputs(cfg, batch, seed=SEED, dtype=torch.float64)

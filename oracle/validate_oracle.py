@@ -29,6 +29,9 @@ CASES = [
     ("swin_t_T2_fusion", dict(img_size=224, num_frames=2, label_dim=29, **O.PRESETS["swin_t"]), 1, "fusion"),
     # BASELINE.json configs[0]: AVE 29-class Swin-T, batch 2, 10 frames 224^2 (the reference's CPU-runnable case)
     ("swin_t_T10_B2_fusion", dict(img_size=224, num_frames=10, label_dim=29, **O.PRESETS["swin_t"]), 2, "fusion"),
+    # the configuration the authors publish (run_adapt_ave29.py:156-165) at FULL depth [2, 2, 18, 2]: heads 4 / 8 / 16 / 32
+    # (window attention in head groups of 2), r = 16 / 32 / 32 / 64, C = 128 .. 1024
+    ("swin_b_T2_B1_fusion", dict(img_size=224, num_frames=2, label_dim=29, **O.PRESETS["swin_b"]), 1, "fusion"),
 ]
 # every case uses bf16-representable weights (make_state docstring): the same fixture then serves the fp32
 # check mode (1e-3) and the bf16 production mode (2e-2) with IDENTICAL weights on both sides

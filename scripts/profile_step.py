@@ -36,6 +36,7 @@ def main():
         opt.step()
 
     m.engine().side_stream_dw = False   # one chain on one stream: the launch list is the whole step, serialised
+    m.engine().graph_mode = "0"         # eager launches (ncu lists them the same either way; keeps the launch order explicit)
     m.engine().lanes = 1
     for _ in range(args.warm):
         step()

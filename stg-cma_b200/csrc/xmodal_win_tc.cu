@@ -181,7 +181,11 @@ __global__ void __launch_bounds__(256) xw_bwd_kernel(const bf16* __restrict__ h,
   float* lse_s = reinterpret_cast<float*>(Ps + 2 * NR * LD);   // [2][64] log2 domain, +inf on padding rows
   float* D_s = lse_s + 2 * NR;                                   // [2][64] gate * <dout, attn_out>
   float* dot_s = D_s + 2 * NR;                                   // [2][64] <dout, attn_out>
-  int* tok = reinterpret_cast<int*>(dot_s + 2 * NR);
+  // per-chunk partial dot products, summed in a FIXED order below: fp32 atomics here made D (and through the bf16 rounding
+  // of dS every gradient upstream of this sub-block) differ from run to run in the last bit -- harmless for the adapters,
+  // but the temporal bias tables amplify it to 0.5 - 0.9 % (tests/test_step_gpu.py::test_full_width_properties)
+  float* part_s = dot_s + 2 * NR;                                // [2][64][CH]
+  int* tok = reinterpret_cast<int*>(part_s + 2 * NR * CH);
   const int N = ws * ws, L = R * R;
   const int nwr = R / ws, nW = nwr * nwr;
   const int w = (int)(blockIdx.x % nW);
@@ -189,7 +193,6 @@ __global__ void __launch_bounds__(256) xw_bwd_kernel(const bf16* __restrict__ h,
   const int wy = w / nwr, wx = w - wy * nwr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   if (tid < NR) tok[tid] = tid < N ? win_token(wy, wx, tid, ws, shift, R) : 0;
-  if (tid < 2 * NR) dot_s[tid] = 0.f;
   __syncthreads();
   const int64_t mod_stride = frames * (int64_t)L * RP;
   for (int e = tid; e < 2 * NR * CH; e += 256) {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(256) xw_bwd_kernel(const bf16* __restrict__ h,
       float dot = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) dot = fmaf(d8[i], a8[i], dot);
-      atomicAdd(&dot_s[mod * NR + r], dot);
+      part_s[(mod * NR + r) * CH + c] = dot;
     } else {
       *reinterpret_cast<uint4*>(hd) = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(dd) = make_uint4(0, 0, 0, 0);
@@ -225,11 +228,13 @@ __global__ void __launch_bounds__(256) xw_bwd_kernel(const bf16* __restrict__ h,
   const uint8_t* ch = Hs + (1 - z) * NR * LD;
   const uint8_t* cd = Ds + (1 - z) * NR * LD;
   const float g_own = gate[z], g_oth = gate[1 - z];
-  if (tid < 2 * NR) D_s[tid] = gate[tid / NR] * dot_s[tid];
-  if (warp < 2) {   // dgate[z] += sum_rows <dout, attn_out>
-    float v = dot_s[warp * NR + lane] + dot_s[warp * NR + lane + 32];
-    v = warp_sum(v);
-    if (lane == 0) atomicAdd(dgate + warp, v);
+  if (tid < 2 * NR) {
+    float d = 0.f;
+    if ((tid & (NR - 1)) < N)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) d += part_s[tid * CH + c];
+    dot_s[tid] = d;
+    D_s[tid] = gate[tid / NR] * d;
   }
 
   uint32_t ha[KS][4], da[KS][4];
@@ -268,6 +273,11 @@ __global__ void __launch_bounds__(256) xw_bwd_kernel(const bf16* __restrict__ h,
     }
   }
   __syncthreads();
+  if (warp < 2) {   // dgate[z] += sum_rows <dout, attn_out>
+    float v = dot_s[warp * NR + lane] + dot_s[warp * NR + lane + 32];
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(dgate + warp, v);
+  }
   const float* col_lse = lse_s + (1 - z) * NR;
   const float* col_D = D_s + (1 - z) * NR;
   const float D0 = D_s[z * NR + row0 + g], D1 = D_s[z * NR + row0 + g + 8];
@@ -383,7 +393,7 @@ template <int RP>
 static int bwd_launch(const void* h, const void* hpre, const float* gate, const void* attn_out, const void* dout, void* dh,
                       float* dgate, int64_t frames, int R, int ws, int shift, cudaStream_t st) {
   constexpr int LD = Cfg<RP>::LD;
-  const size_t smem = (size_t)8 * NR * LD + 6 * NR * sizeof(float) + NR * sizeof(int);
+  const size_t smem = (size_t)8 * NR * LD + (6 + 2 * Cfg<RP>::CH) * NR * sizeof(float) + NR * sizeof(int);
   auto kern = xw_bwd_kernel<RP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("xmodal_window_bwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }

@@ -33,6 +33,9 @@ def _rup(x, m):
     return (x + m - 1) // m * m
 
 
+_POISON = os.environ.get("STGCMA_POISON", "0") == "1"
+
+
 class _Arena:
     """Named persistent device buffers; a slot is re-allocated only when its shape/dtype changes."""
 
@@ -44,6 +47,8 @@ class _Arena:
         shape = tuple(int(s) for s in shape)
         if t is None or tuple(t.shape) != shape or t.dtype != dtype or t.device != device:
             t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            if _POISON and not zero and t.is_floating_point():
+                t.fill_(float("nan"))   # debug: a kernel that reads a buffer before anything wrote it shows up as NaN
             self.slots[name] = t
         return t
 
@@ -76,6 +81,14 @@ class SwinAVEEngine:
         # kernels of the main chain, and is joined before its operand buffers are rewritten (backward())
         self.side_stream_dw = os.environ.get("STGCMA_SIDE_DW", "1") != "0"
         self._side = {}
+        # CUDA graphs: a step is ~510 launches (plus the torch ops around them); below ~8 clips per GPU the host cannot
+        # enqueue them as fast as the GPU retires them (BASELINE configs[0] runs 2 clips; the authors trained with 1-3).
+        # The forward and the backward schedules are captured once per (mode, shape, flags) after two eager warm-up steps
+        # and replayed: every buffer lives in the persistent arena, so the captured addresses stay valid.
+        # STGCMA_GRAPH=1: always, 0: never, default: steps of <= 8 clips.
+        self.graph_mode = os.environ.get("STGCMA_GRAPH", "auto")
+        self.graph_max_clips = 8
+        self._graphs = {}
 
     @property
     def arena(self):
@@ -278,7 +291,6 @@ class SwinAVEEngine:
             self._check_frozen()
         fz = self._build_frozen(dev, adt)
         pk = self._build_train_pack(dev, adt)
-        L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
         self.generation += 1
         B, Cin, T, H, W = v.shape
         assert Cin == 3 and T == cfg.num_frames and H == cfg.img_size and W == cfg.img_size, "video must be [B,3,T,H,W]"
@@ -288,6 +300,9 @@ class SwinAVEEngine:
         lanes = min(self.lanes, B) if dev.type == "cuda" else 1
         while len(self.arenas) < lanes:
             self.arenas.append(_Arena())
+        if self._graph_wanted(B, dev, lanes):
+            return self._forward_graphed(a32, v32, mode, need_grad, fz, pk)
+        L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
         if lanes == 1:
             logits, part = self._forward_part(a32, v32, mode, self.arenas[0], fz, pk)
             return logits, dict(gen=self.generation, mode=mode, dev=dev, parts=[part], rows=[(0, B * T)])
@@ -315,6 +330,69 @@ class SwinAVEEngine:
         for st in self._lane_streams[1:lanes]:
             a32.record_stream(st); v32.record_stream(st)
         return torch.cat(outs, 0), dict(gen=self.generation, mode=mode, dev=dev, parts=parts, rows=rows)
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the two schedules
+    # ------------------------------------------------------------------------------------------
+    def _graph_wanted(self, B, dev, lanes):
+        if dev.type != "cuda" or lanes != 1 or self.graph_mode == "0" or L_.profiling():
+            return False
+        return self.graph_mode == "1" or B <= self.graph_max_clips
+
+    def _forward_graphed(self, a32, v32, mode, need_grad, fz, pk):
+        m = self.m
+        dev, adt = v32.device, m.compute_dtype
+        B, T = v32.shape[0], v32.shape[2]
+        key = (mode, bool(need_grad), m.training, m.mlp_head[1].training, tuple(v32.shape), dev.index, adt, self.side_stream_dw)
+        ent = self._graphs.get(key)
+        if ent is None or ent["fz"] is not fz or ent["pk"] is not pk:
+            # (new weights caches invalidate the captured addresses: start over)
+            ent = self._graphs[key] = dict(fz=fz, pk=pk, seen=0, fwd=None, bwd=None)
+        sv = dict(gen=self.generation, mode=mode, dev=dev, rows=[(0, B * T)], graph=None)
+        if ent["seen"] < 2:                      # eager warm-up: arena allocation, kernel attributes, lazy module loading
+            ent["seen"] += 1
+            L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
+            logits, part = self._forward_part(a32, v32, mode, self.arenas[0], fz, pk)
+            sv["parts"] = [part]
+            return logits, sv
+        if ent["fwd"] is None:
+            ent["a"], ent["v"] = a32.clone(), v32.clone()       # static inputs of the captured schedule
+            torch.cuda.current_stream(dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L_.launches()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
+                logits, part = self._forward_part(ent["a"], ent["v"], mode, self.arenas[0], fz, pk)
+            ent.update(fwd=g, logits=logits, part=part, fwd_launches=L_.launches() - n0)
+            L_.add_launches(-ent["fwd_launches"])               # capture launches nothing; the replay below is counted
+        else:
+            ent["a"].copy_(a32)
+            ent["v"].copy_(v32)
+        ent["fwd"].replay()
+        L_.add_launches(ent["fwd_launches"])
+        sv["parts"], sv["graph"] = [ent["part"]], ent
+        return ent["logits"].clone(), sv
+
+    def _backward_graphed(self, ent, sv, dlogits):
+        dev, pk = sv["dev"], self.train_pack
+        dl = dlogits.detach().to(torch.float32).contiguous()
+        if ent["bwd"] is None:
+            ent["dlogits"] = dl.clone()
+            gbuf = self.arenas[0].get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
+            torch.cuda.current_stream(dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L_.launches()
+            with torch.cuda.graph(g, pool=ent["fwd"].pool(), capture_error_mode="thread_local"):
+                gbuf.zero_()
+                self._backward_part(ent["part"], ent["dlogits"], gbuf)
+                out = gbuf.clone()
+            ent.update(bwd=g, gout=out, bwd_launches=L_.launches() - n0)
+            L_.add_launches(-ent["bwd_launches"])
+        else:
+            ent["dlogits"].copy_(dl)
+        ent["bwd"].replay()
+        L_.add_launches(ent["bwd_launches"])
+        return ent["gout"].clone()   # never hand autograd a view of the static buffer (gradient accumulation would alias it)
 
     def saved_masks(self, sv):
         """DropPath masks {(stage, block): flat [2, B, T, L]} and the head-dropout keep mask [B*T, hidden] of a forward,
@@ -489,10 +567,16 @@ class SwinAVEEngine:
                                  "(run forward -> backward -> forward ...)")
         dev = sv["dev"]
         pk = self.train_pack
-        gbuf = self.arenas[0].get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
-        gbuf.zero_()
         parts = sv["parts"]
-        if len(parts) == 1:
+        gbuf = None
+        if sv.get("graph") is not None:
+            out = self._backward_graphed(sv["graph"], sv, dlogits)
+        else:
+            gbuf = self.arenas[0].get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
+            gbuf.zero_()
+        if gbuf is None:
+            pass
+        elif len(parts) == 1:
             self._backward_part(parts[0], dlogits, gbuf)
         else:
             main = torch.cuda.current_stream(dev)
@@ -507,7 +591,8 @@ class SwinAVEEngine:
                     done.record(st)
                 main.wait_event(done)
                 dlogits.record_stream(st)
-        out = gbuf.clone()
+        if gbuf is not None:
+            out = gbuf.clone()
         if self.dp_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(out)

@@ -84,6 +84,16 @@ def launches():
     return _launches
 
 
+def add_launches(n):
+    """CUDA-graph replays launch the captured kernels without passing through _call (engine.py)."""
+    global _launches
+    _launches += n
+
+
+def profiling():
+    return _prof is not None
+
+
 def dt(t_or_dtype):
     d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
     if d == torch.float32:
