@@ -19,7 +19,7 @@ import os
 import torch
 
 from . import lib as L_
-from .engine import _Arena, _rup, _EPS_PAD
+from .engine import _Arena, _StepGraphs, _rup, _EPS_PAD
 
 
 class ClipAVEEngine:
@@ -35,10 +35,23 @@ class ClipAVEEngine:
         self.dp_allreduce = True
         self.side_stream_dw = os.environ.get("STGCMA_SIDE_DW", "1") != "0"
         self._side = {}
+        self.graphs = _StepGraphs()   # CUDA-graph replay of the schedules for launch-bound steps (engine._StepGraphs)
 
     @property
     def arena(self):
         return self.arena_
+
+    @property
+    def graph_mode(self):
+        return self.graphs.mode
+
+    @graph_mode.setter
+    def graph_mode(self, v):
+        self.graphs.mode = v
+
+    @property
+    def _graphs(self):
+        return self.graphs.entries
 
     @staticmethod
     def stream_dtype(adt):
@@ -208,7 +221,6 @@ class ClipAVEEngine:
             self._check_frozen()
         fz = self._build_frozen(dev, adt)
         pk = self._build_train_pack(dev, adt)
-        L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
         self.generation += 1
         B, Cin, T, H, W = v.shape
         Ha, Wa = cfg.audio_shape
@@ -217,8 +229,17 @@ class ClipAVEEngine:
         assert tuple(a.shape) == (B, T, Ha, Wa), f"audio must be [B,T,{Ha},{Wa}] (CLIP path)"
         a32 = a.detach().to(torch.float32).contiguous()
         v32 = v.detach().to(torch.float32).contiguous()
-        logits, part = self._forward_part(a32, v32, mode, fz, pk)
-        part["gen"] = self.generation
+
+        def run(a_, v_):
+            L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
+            return self._forward_part(a_, v_, mode, fz, pk)
+        ent = None
+        if self.graphs.wanted(B, dev):
+            key = (mode, bool(need_grad), m.training, m.mlp_head[1].training, tuple(v32.shape), dev.index, adt, self.side_stream_dw)
+            logits, part, ent = self.graphs.forward(key, fz, pk, a32, v32, run)
+        else:
+            logits, part = run(a32, v32)
+        part["gen"], part["graph"] = self.generation, ent
         return logits, part
 
     def saved_masks(self, sv):
@@ -374,9 +395,12 @@ class ClipAVEEngine:
         dev = sv["dev"]
         pk = self.train_pack
         gbuf = self.arena_.get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
-        gbuf.zero_()
-        self._backward_part(sv, dlogits, gbuf)
-        out = gbuf.clone()
+        if sv.get("graph") is not None:
+            out = self.graphs.backward(sv["graph"], dlogits, gbuf, self._backward_part)
+        else:
+            gbuf.zero_()
+            self._backward_part(sv, dlogits, gbuf)
+            out = gbuf.clone()
         if self.dp_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(out)

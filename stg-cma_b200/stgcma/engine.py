@@ -59,6 +59,73 @@ class _Arena:
         self.slots.clear()
 
 
+class _StepGraphs:
+    """CUDA-graph capture / replay of an engine's forward and backward schedules (shared by the Swin and CLIP engines).
+
+    A step is 500 - 800 launches plus the torch ops around them; below ~8 clips per GPU the host cannot enqueue them as
+    fast as the GPU retires them (BASELINE configs[0] runs 2 clips; the authors trained with 1 - 3).  Each schedule is
+    captured once per (mode, shape, flags) key after two eager warm-up steps (arena allocation, kernel attributes, lazy
+    module loading) and replayed: every buffer lives in the persistent arena, so the captured addresses stay valid; the
+    DropPath / dropout masks are drawn inside the captured schedule by torch's graph-safe generator.
+    STGCMA_GRAPH=1: always, 0: never, default: steps of <= 8 clips."""
+
+    def __init__(self):
+        self.mode = os.environ.get("STGCMA_GRAPH", "auto")
+        self.max_clips = 8
+        self.entries = {}
+
+    def wanted(self, B, dev):
+        if dev.type != "cuda" or self.mode == "0" or L_.profiling():
+            return False
+        return self.mode == "1" or B <= self.max_clips
+
+    def forward(self, key, fz, pk, a32, v32, run):
+        """run(a, v) -> (logits, part) launches the forward schedule.  Returns (logits, part, entry or None)."""
+        ent = self.entries.get(key)
+        if ent is None or ent["fz"] is not fz or ent["pk"] is not pk:
+            # (new weight caches invalidate the captured addresses: start over)
+            ent = self.entries[key] = dict(fz=fz, pk=pk, seen=0, fwd=None, bwd=None)
+        if ent["seen"] < 2:
+            ent["seen"] += 1
+            logits, part = run(a32, v32)
+            return logits, part, None
+        if ent["fwd"] is None:
+            ent["a"], ent["v"] = a32.clone(), v32.clone()       # static inputs of the captured schedule
+            torch.cuda.current_stream(v32.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L_.launches()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                logits, part = run(ent["a"], ent["v"])
+            ent.update(fwd=g, logits=logits, part=part, fwd_launches=L_.launches() - n0)
+            L_.add_launches(-ent["fwd_launches"])               # capture launches nothing; the replay below is counted
+        else:
+            ent["a"].copy_(a32)
+            ent["v"].copy_(v32)
+        ent["fwd"].replay()
+        L_.add_launches(ent["fwd_launches"])
+        return ent["logits"].clone(), ent["part"], ent
+
+    def backward(self, ent, dlogits, gbuf, run):
+        """run(part, dlogits, gbuf) launches the backward schedule into the (zeroed) bucket.  -> a fresh copy of the bucket."""
+        dl = dlogits.detach().to(torch.float32).contiguous()
+        if ent["bwd"] is None:
+            ent["dlogits"] = dl.clone()
+            torch.cuda.current_stream(dl.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L_.launches()
+            with torch.cuda.graph(g, pool=ent["fwd"].pool(), capture_error_mode="thread_local"):
+                gbuf.zero_()
+                run(ent["part"], ent["dlogits"], gbuf)
+                out = gbuf.clone()
+            ent.update(bwd=g, gout=out, bwd_launches=L_.launches() - n0)
+            L_.add_launches(-ent["bwd_launches"])
+        else:
+            ent["dlogits"].copy_(dl)
+        ent["bwd"].replay()
+        L_.add_launches(ent["bwd_launches"])
+        return ent["gout"].clone()   # never hand autograd a view of the static buffer (gradient accumulation would alias it)
+
+
 class SwinAVEEngine:
     def __init__(self, module):
         self.m = module  # the nn.Module that owns the fp32 master parameters (model/Swin_AVE.py)
@@ -81,14 +148,7 @@ class SwinAVEEngine:
         # kernels of the main chain, and is joined before its operand buffers are rewritten (backward())
         self.side_stream_dw = os.environ.get("STGCMA_SIDE_DW", "1") != "0"
         self._side = {}
-        # CUDA graphs: a step is ~510 launches (plus the torch ops around them); below ~8 clips per GPU the host cannot
-        # enqueue them as fast as the GPU retires them (BASELINE configs[0] runs 2 clips; the authors trained with 1-3).
-        # The forward and the backward schedules are captured once per (mode, shape, flags) after two eager warm-up steps
-        # and replayed: every buffer lives in the persistent arena, so the captured addresses stay valid.
-        # STGCMA_GRAPH=1: always, 0: never, default: steps of <= 8 clips.
-        self.graph_mode = os.environ.get("STGCMA_GRAPH", "auto")
-        self.graph_max_clips = 8
-        self._graphs = {}
+        self.graphs = _StepGraphs()
 
     @property
     def arena(self):
@@ -300,7 +360,7 @@ class SwinAVEEngine:
         lanes = min(self.lanes, B) if dev.type == "cuda" else 1
         while len(self.arenas) < lanes:
             self.arenas.append(_Arena())
-        if self._graph_wanted(B, dev, lanes):
+        if lanes == 1 and self.graphs.wanted(B, dev):
             return self._forward_graphed(a32, v32, mode, need_grad, fz, pk)
         L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
         if lanes == 1:
@@ -331,68 +391,30 @@ class SwinAVEEngine:
             a32.record_stream(st); v32.record_stream(st)
         return torch.cat(outs, 0), dict(gen=self.generation, mode=mode, dev=dev, parts=parts, rows=rows)
 
-    # ------------------------------------------------------------------------------------------
-    # CUDA-graph replay of the two schedules
-    # ------------------------------------------------------------------------------------------
-    def _graph_wanted(self, B, dev, lanes):
-        if dev.type != "cuda" or lanes != 1 or self.graph_mode == "0" or L_.profiling():
-            return False
-        return self.graph_mode == "1" or B <= self.graph_max_clips
+    # graph_mode / _graphs: test and script hooks (tests/test_step_gpu.py, scripts/profile_step.py)
+    @property
+    def graph_mode(self):
+        return self.graphs.mode
+
+    @graph_mode.setter
+    def graph_mode(self, v):
+        self.graphs.mode = v
+
+    @property
+    def _graphs(self):
+        return self.graphs.entries
 
     def _forward_graphed(self, a32, v32, mode, need_grad, fz, pk):
         m = self.m
         dev, adt = v32.device, m.compute_dtype
         B, T = v32.shape[0], v32.shape[2]
         key = (mode, bool(need_grad), m.training, m.mlp_head[1].training, tuple(v32.shape), dev.index, adt, self.side_stream_dw)
-        ent = self._graphs.get(key)
-        if ent is None or ent["fz"] is not fz or ent["pk"] is not pk:
-            # (new weights caches invalidate the captured addresses: start over)
-            ent = self._graphs[key] = dict(fz=fz, pk=pk, seen=0, fwd=None, bwd=None)
-        sv = dict(gen=self.generation, mode=mode, dev=dev, rows=[(0, B * T)], graph=None)
-        if ent["seen"] < 2:                      # eager warm-up: arena allocation, kernel attributes, lazy module loading
-            ent["seen"] += 1
-            L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
-            logits, part = self._forward_part(a32, v32, mode, self.arenas[0], fz, pk)
-            sv["parts"] = [part]
-            return logits, sv
-        if ent["fwd"] is None:
-            ent["a"], ent["v"] = a32.clone(), v32.clone()       # static inputs of the captured schedule
-            torch.cuda.current_stream(dev).synchronize()
-            g = torch.cuda.CUDAGraph()
-            n0 = L_.launches()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
-                logits, part = self._forward_part(ent["a"], ent["v"], mode, self.arenas[0], fz, pk)
-            ent.update(fwd=g, logits=logits, part=part, fwd_launches=L_.launches() - n0)
-            L_.add_launches(-ent["fwd_launches"])               # capture launches nothing; the replay below is counted
-        else:
-            ent["a"].copy_(a32)
-            ent["v"].copy_(v32)
-        ent["fwd"].replay()
-        L_.add_launches(ent["fwd_launches"])
-        sv["parts"], sv["graph"] = [ent["part"]], ent
-        return ent["logits"].clone(), sv
 
-    def _backward_graphed(self, ent, sv, dlogits):
-        dev, pk = sv["dev"], self.train_pack
-        dl = dlogits.detach().to(torch.float32).contiguous()
-        if ent["bwd"] is None:
-            ent["dlogits"] = dl.clone()
-            gbuf = self.arenas[0].get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
-            torch.cuda.current_stream(dev).synchronize()
-            g = torch.cuda.CUDAGraph()
-            n0 = L_.launches()
-            with torch.cuda.graph(g, pool=ent["fwd"].pool(), capture_error_mode="thread_local"):
-                gbuf.zero_()
-                self._backward_part(ent["part"], ent["dlogits"], gbuf)
-                out = gbuf.clone()
-            ent.update(bwd=g, gout=out, bwd_launches=L_.launches() - n0)
-            L_.add_launches(-ent["bwd_launches"])
-        else:
-            ent["dlogits"].copy_(dl)
-        ent["bwd"].replay()
-        L_.add_launches(ent["bwd_launches"])
-        return ent["gout"].clone()   # never hand autograd a view of the static buffer (gradient accumulation would alias it)
+        def run(a, v):
+            L_.pack_params(pk["_table"], pk["_n"], L_.dt(adt))
+            return self._forward_part(a, v, mode, self.arenas[0], fz, pk)
+        logits, part, ent = self.graphs.forward(key, fz, pk, a32, v32, run)
+        return logits, dict(gen=self.generation, mode=mode, dev=dev, rows=[(0, B * T)], parts=[part], graph=ent)
 
     def saved_masks(self, sv):
         """DropPath masks {(stage, block): flat [2, B, T, L]} and the head-dropout keep mask [B*T, hidden] of a forward,
@@ -568,11 +590,11 @@ class SwinAVEEngine:
         dev = sv["dev"]
         pk = self.train_pack
         parts = sv["parts"]
-        gbuf = None
+        gbuf = self.arenas[0].get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
         if sv.get("graph") is not None:
-            out = self._backward_graphed(sv["graph"], sv, dlogits)
+            out = self.graphs.backward(sv["graph"], dlogits, gbuf, self._backward_part)
+            gbuf = None
         else:
-            gbuf = self.arenas[0].get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
             gbuf.zero_()
         if gbuf is None:
             pass

@@ -162,3 +162,37 @@ def test_full_width_properties():
         f0 = m(a.cuda(), v.cuda(), "fusion").cpu()
         mm = m(a.cuda(), v.cuda(), "multimodal").cpu()
     assert rel(f0, mm) < 1e-6 or torch.equal(f0, mm)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cuda_graph_replay_matches_eager(dtype):
+    """Launch-bound steps (<= 8 clips, ~800 launches) replay the captured schedules (engine._StepGraphs); six training steps
+    with fresh inputs, DropPath off, and an optimizer update in between agree with the eager schedule."""
+    from stgcma.optim import FusedAdam
+    cfg = C.ClipAVEConfig(**TINY)
+    sd = C.make_state(cfg, seed=7, bf16_exact=True)
+    models, opts = [], []
+    for mode in ("0", "1"):
+        m = build(TINY, "fusion", dtype, sd)
+        m.engine().graph_mode = mode
+        models.append(m)
+        opts.append(FusedAdam([p for p in m.parameters() if p.requires_grad], lr=1e-3, betas=(0.95, 0.999), weight_decay=5e-7))
+    tol = 1e-4 if dtype == torch.float32 else 1e-2   # bf16: last-bit differences of the atomically reduced dW flip roundings
+    for it in range(6):
+        a, v, labels = C.make_inputs(cfg, 2, seed=100 + it)
+        outs = []
+        for m, opt in zip(models, opts):
+            opt.zero_grad(set_to_none=True)
+            out = m(a.cuda(), v.cuda(), "fusion")
+            torch.nn.CrossEntropyLoss()(out, labels.cuda()).backward()
+            opt.step()
+            outs.append(out.detach().float().cpu())
+        assert rel(outs[1], outs[0]) < tol, it
+    torch.cuda.synchronize()
+    ent = next(iter(models[1].engine()._graphs.values()))
+    assert ent["fwd"] is not None and ent["bwd"] is not None and ent["fwd_launches"] > 50 and ent["bwd_launches"] > 50
+    assert not models[0].engine()._graphs
+    p0, p1 = dict(models[0].named_parameters()), dict(models[1].named_parameters())
+    for n, p in p0.items():
+        if p.requires_grad:
+            assert rel(p1[n].detach().cpu(), p.detach().cpu()) < tol, n
