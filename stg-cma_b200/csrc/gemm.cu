@@ -212,10 +212,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
 // =========================================================================================
 namespace tc {
 
-constexpr int kEpiWarps = 8;             // two warps per TMEM lane quarter, alternating 32-column chunks
-constexpr int kThreads = 64 + kEpiWarps * 32;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
+// Epilogue warps: two per TMEM lane quarter, alternating 32-column chunks -- or four (OCC = 3: one CTA per SM with 16
+// epilogue warps) for the wide-N shapes with K < 1024 whose epilogue, not the MMA, sets the tile time.
+constexpr int epi_warps(int occ) { return occ == 3 ? 16 : 8; }
 constexpr int kStageRowF = 36;           // staging row stride in floats (32 + 4 pad: conflict-free 128-bit rows)
-constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowF * 4;
+constexpr int staging_bytes(int occ) { return epi_warps(occ) * 32 * kStageRowF * 4; }
 constexpr int kABytes = BM * BK * 2;     // 16 KiB
 
 struct Params {
@@ -230,12 +231,13 @@ struct Params {
 // small-K, epilogue-bound shapes: two tiles in flight per SM hide the epilogue latency; OCC = 1 (BN <= 256) for the
 // large-K, tensor-bound ones (a 128 x 256 tile reads 25 % less shared memory per flop than two 128 x 128 tiles).
 template <int MODE, bool OUT_F32, int NRES, int OCC, bool TMAOUT>
-__global__ void __launch_bounds__(kThreads, OCC)
+__global__ void __launch_bounds__(64 + epi_warps(OCC) * 32, OCC == 3 ? 1 : OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for SWIZZLE_128B, by pointer arithmetic on the shared pointer (keeps ld/st.shared addressing)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kEpiWarps = epi_warps(OCC), kStagingBytes = staging_bytes(OCC);
   const uint32_t stage_bytes = kABytes + (uint32_t)p.BN * 128u;
   float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + kStagingBytes);
@@ -325,7 +327,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== epilogue warps (TMEM -> regs -> smem transpose -> global) =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int par = (warp - 2) >> 2;    // 0: even 32-column chunks, 1: odd chunks
+    const int par = (warp - 2) >> 2;    // chunks par, par + NPAR, ... of the tile
+    constexpr int NPAR = kEpiWarps / 4;
     const int nchunks = (p.BN + 31) >> 5;
     float* stg = staging + (size_t)(warp - 2) * 32 * kStageRowF;
     const EpiParams ep = p.epi;
@@ -352,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
         first = false;
-        for (int ch = par; ch < nchunks; ch += 2) {
+        for (int ch = par; ch < nchunks; ch += NPAR) {
           const int c0 = ch << 5;
           const bool wide = p.BN - c0 >= 32;
           float v[32];
@@ -405,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + acc * (uint32_t)p.BN + ((uint32_t)(q * 32) << 16);
       const int64_t wrow = (int64_t)m_blk * BM + q * 32;   // first row (within the group) of this warp
       bool waited = false;
-      for (int ch = par; ch < nchunks; ch += 2) {
+      for (int ch = par; ch < nchunks; ch += NPAR) {
         const int c0 = ch << 5;
         const bool wide = p.BN - c0 >= 32;
         const int lpr = wide ? 4 : 2;       // lanes per row (8 columns each)
@@ -433,7 +436,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
         if (wide) tmem_ld32(t_row + (uint32_t)c0, v);
         else tmem_ld16(t_row + (uint32_t)c0, v);
-        if (ch + 2 >= nchunks) {
+        if (ch + NPAR >= nchunks) {
           // all TMEM reads of this warp for this accumulator are done: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
@@ -491,8 +494,14 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   // 775 -> 859 TFLOP/s, qkv stage 3 908 -> 1176, proj stage 3 780 -> 961; mlp.fc1 + GELU stage 2 532 -> 509 (kept at 2).
   const bool act_epi = ep.mode == STGCMA_EPI_GELU || ep.mode == STGCMA_EPI_DGELU || ep.mode == STGCMA_EPI_QGELU ||
                        ep.mode == STGCMA_EPI_DQGELU || ep.mode == STGCMA_EPI_GELU_G || ep.mode == STGCMA_EPI_QGELU_G;
-  const int occ = (K >= 1024 || (K >= 256 && N >= 384 && (!act_epi || K >= 768))) ? 1 : 2;
-  const int bn_max = occ == 1 ? 256 : 128;
+  int occ = (K >= 1024 || (K >= 256 && N >= 384 && (!act_epi || K >= 768))) ? 1 : 2;
+  // wide-N outputs behind a short K: a 128 x 256 tile's MMAs take ~3 k cycles at K = 384 while 8 epilogue warps need 2 - 4x
+  // that to drain it (TMEM -> transpose -> GELU' / aux multiply -> two [M, N] tensors): 16 epilogue warps per CTA
+  static const int epw16 = getenv("STGCMA_GEMM_EPW16") ? atoi(getenv("STGCMA_GEMM_EPW16")) : 1;
+  // measured (scripts/gemm_shapes.py, 64 clips): fc1 + GELU' stage 2 3.50 -> 3.16 ms, its MULAUX backward 3.61 -> 3.13 ms, the
+  // stage-3 pair 0.70 / 0.68 -> 0.66 / 0.61 ms; the plain wide-N GEMMs (qkv) lose 1 - 4 % to the shallower ring: not routed here
+  if (epw16 && ep.mode != STGCMA_EPI_LINEAR && K >= 256 && K < 1024 && N >= 1024) occ = 3;
+  const int bn_max = occ != 2 ? 256 : 128;
   int best_bn = 16;
   int64_t best_cost = -1;
   for (int bn = bn_max; bn >= 16; bn -= 16) {
@@ -511,7 +520,8 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   p.num_tiles = (int)tiles;
   p.k_blocks = (int)ceil_div(K, BK);
   const int stage_bytes = kABytes + p.BN * 128;
-  const int smem_cap = occ == 1 ? 232448 : (233472 / 2 - 1024);   // per CTA; 1 KB per CTA is reserved by the driver
+  const int smem_cap = occ != 2 ? 232448 : (233472 / 2 - 1024);   // per CTA; 1 KB per CTA is reserved by the driver
+  const int kStagingBytes = staging_bytes(occ), kThreads = 64 + epi_warps(occ) * 32;
   const int budget = smem_cap - 1024 - kStagingBytes - 256;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
@@ -536,7 +546,8 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   }
 
   const size_t smem = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 256;
-  const int grid = p.num_tiles < occ * sm_count() ? p.num_tiles : occ * sm_count();
+  const int ctas_per_sm = occ == 2 ? 2 : 1;
+  const int grid = p.num_tiles < ctas_per_sm * sm_count() ? p.num_tiles : ctas_per_sm * sm_count();
   const int nres = (ep.mode == STGCMA_EPI_LINEAR) ? (ep.res1 ? (ep.res2 ? 2 : 1) : 0) : 0;
   if (ep.mode == STGCMA_EPI_LINEAR && ep.res2 && !ep.res1) {
     set_error("gemm(bf16): res2 without res1 is not supported");
@@ -544,6 +555,7 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   }
 #define STG_TC_LAUNCH(MODE_, F32_, NRES_)                                                                      \
   do {                                                                                                         \
+    if (occ == 3) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 3, false);                                                \
     if (occ == 1) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 1, false);                                                \
     STG_TC_LAUNCH2(MODE_, F32_, NRES_, 2, false);                                                              \
   } while (0)
@@ -552,7 +564,7 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
     auto kern = gemm_tc_kernel<MODE_, F32_, NRES_, OCC_, TMA_>;                                                    \
     static std::once_flag once;                                                                                \
     static cudaError_t attr_err = cudaSuccess;                                                                 \
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCC_ == 1 ? 232448 : 115712); }); \
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCC_ != 2 ? 232448 : 115712); }); \
     if (attr_err != cudaSuccess) {                                                                             \
       set_error("gemm: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));                    \
       return STGCMA_ECUDA;                                                                                     \
@@ -563,7 +575,7 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   const bool f32 = ep.out_f32 != 0;
   if (tma_out) {
     if (occ == 1) STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 1, true);
-    STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 2, true);
+    if (occ == 2) STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 2, true);
   }
   switch (ep.mode) {
     case STGCMA_EPI_LINEAR:
