@@ -229,6 +229,16 @@ typedef struct StgcmaAdamGroups {
 } StgcmaAdamGroups;
 int stgcma_adam_step(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host, float grad_scale,
                      void* stream);
+/* The same step under torch.amp.GradScaler (the caller's loop, traintest_adapt_ave29.py:158-168) WITHOUT the scaler's
+ * separate unscale pass and WITHOUT its per-step host read of found_inf: `scale_dev` (the scaler's current scale) and
+ * `found_inf_dev` (1.0 when a gradient is inf / nan) are DEVICE scalars read by the kernel, as in torch's own fused Adam
+ * (the optimizer advertises `_step_supports_amp_scaling`).  Gradients are divided by *scale_dev and written back
+ * un-scaled; when *found_inf_dev != 0 nothing is updated and *skipped_dev (int32, cumulative) is incremented, so the
+ * bias corrections -- computed in the kernel from steps_host[group] - *skipped_dev -- do not advance either.
+ * groups_host->bias_corr1 / bias_corr2_sqrt are ignored.                                                           */
+int stgcma_adam_step_amp(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host,
+                         const int32_t* steps_host /* [STGCMA_ADAM_MAX_GROUPS] */, const float* scale_dev,
+                         const float* found_inf_dev, int32_t* skipped_dev, void* stream);
 
 /* ==== CLIP-ViT variant of the step (MM_CLIP_AVE, AVE/model/CLIP_AVE.py:716; BASELINE.json configs[1]) ================
 

@@ -545,9 +545,62 @@ __global__ void __launch_bounds__(256) adam_kernel(const StgcmaAdamEntry* __rest
   }
 }
 
+// GradScaler variant: scale / found_inf are device scalars, bias corrections from the device-side count of applied steps
+struct AdamSteps { int32_t t[STGCMA_ADAM_MAX_GROUPS]; };
+__global__ void __launch_bounds__(256) adam_amp_kernel(const StgcmaAdamEntry* __restrict__ table, const StgcmaAdamGroups hp,
+                                                       const AdamSteps steps, const float* __restrict__ scale,
+                                                       const float* __restrict__ found_inf, int32_t* __restrict__ skipped) {
+  // every block reads *skipped BEFORE the barrier-free early exit below can change it: only the found_inf path writes it,
+  // and on that path nobody uses the value
+  const int skipped_now = *skipped;
+  if (*found_inf != 0.f) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *skipped = skipped_now + 1;
+    return;
+  }
+  const StgcmaAdamEntry e = table[blockIdx.x];
+  const int gi = e.group;
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(steps.t[gi] - skipped_now);
+    s_bc[0] = (float)(1.0 - pow((double)hp.beta1[gi], t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)hp.beta2[gi], t));
+  }
+  __syncthreads();
+  const float lr = hp.lr[gi], wd = hp.weight_decay[gi], b2 = hp.beta2[gi], eps = hp.eps[gi];
+  const float step_size = lr / s_bc[0], bc2s = s_bc[1];
+  const float omb1 = hp.one_minus_beta1[gi], omb2 = hp.one_minus_beta2[gi];
+  const float inv = 1.0f / *scale;
+  float* grad_rw = const_cast<float*>(e.grad);
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e.numel; i += (int64_t)gridDim.y * blockDim.x) {
+    const float p = e.param[i];
+    float g = e.grad[i] * inv;
+    grad_rw[i] = g;                                       // torch's fused Adam leaves the un-scaled gradient behind
+    g = fmaf(wd, p, g);
+    const float m = fmaf(omb1, g - e.exp_avg[i], e.exp_avg[i]);
+    const float v = fmaf(omb2 * g, g, b2 * e.exp_avg_sq[i]);
+    e.exp_avg[i] = m;
+    e.exp_avg_sq[i] = v;
+    const float denom = sqrtf(v) / bc2s + eps;
+    e.param[i] = p - step_size * (m / denom);
+  }
+}
+
 }  // namespace stgcma
 
 using namespace stgcma;
+
+extern "C" int stgcma_adam_step_amp(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host,
+                                    const int32_t* steps_host, const float* scale_dev, const float* found_inf_dev,
+                                    int32_t* skipped_dev, void* stream) {
+  STG_REQUIRE(n > 0 && table_dev && groups_host && steps_host, "adam_step_amp: empty table");
+  STG_REQUIRE(scale_dev && found_inf_dev && skipped_dev, "adam_step_amp: scale / found_inf / skipped must be device pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamSteps steps;
+  for (int i = 0; i < STGCMA_ADAM_MAX_GROUPS; ++i) steps.t[i] = steps_host[i];
+  dim3 grid(n, 16);
+  adam_amp_kernel<<<grid, 256, 0, st>>>(table_dev, *groups_host, steps, scale_dev, found_inf_dev, skipped_dev);
+  return check_launch("adam_step_amp");
+}
 
 extern "C" int stgcma_adam_step(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host, float grad_scale,
                                 void* stream) {

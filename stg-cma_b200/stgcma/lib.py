@@ -40,6 +40,7 @@ _SIGNATURES = {
     "stgcma_head_pool_bwd": [_vp, _vp, _i64, _i, _i, _i, _vp],
     "stgcma_pack_params": [_vp, _i, _i, _vp],
     "stgcma_adam_step": [_vp, _i, _vp, ctypes.c_float, _vp],
+    "stgcma_adam_step_amp": [_vp, _i, _vp, _vp, _fp, _fp, _vp, _vp],
     "stgcma_mha_fwd": [_vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_mha_bwd": [_vp, _vp, _fp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_im2col": [_fp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i, _vp],
@@ -368,6 +369,22 @@ def adam_step(table_dev, n, groups, grad_scale=1.0, numel=0):
     hp = (ctypes.c_float * len(flat))(*flat)      # StgcmaAdamGroups, passed by host pointer
     _call("stgcma_adam_step", _p(table_dev), n, ctypes.cast(hp, ctypes.c_void_p), ctypes.c_float(grad_scale),
           cost=(0.0, 28.0 * numel))
+
+
+def adam_step_amp(table_dev, n, groups, steps, scale_dev, found_inf_dev, skipped_dev, numel=0):
+    """Adam under GradScaler: `scale_dev` / `found_inf_dev` are the scaler's device scalars, `skipped_dev` an int32 device
+    counter of skipped steps; `steps` = host step count per group slot (bias corrections are computed in the kernel)."""
+    if len(groups) > ADAM_MAX_GROUPS:
+        raise StgcmaError(f"adam_step: at most {ADAM_MAX_GROUPS} parameter groups")
+    fields = ("lr", "weight_decay", "beta1", "beta2", "eps", "bias_corr1", "bias_corr2_sqrt", "one_minus_beta1", "one_minus_beta2")
+    flat = []
+    for f in fields:
+        vals = [float(g[f]) if f in g else (1.0 - float(g["beta" + f[-1]]) if f.startswith("one_minus") else 1.0) for g in groups]
+        flat += vals + [1.0] * (ADAM_MAX_GROUPS - len(vals))
+    hp = (ctypes.c_float * len(flat))(*flat)
+    st = (ctypes.c_int32 * ADAM_MAX_GROUPS)(*([int(t) for t in steps] + [1] * (ADAM_MAX_GROUPS - len(steps))))
+    _call("stgcma_adam_step_amp", _p(table_dev), n, ctypes.cast(hp, ctypes.c_void_p), ctypes.cast(st, ctypes.c_void_p),
+          _p(scale_dev), _p(found_inf_dev), _p(skipped_dev), cost=(0.0, 32.0 * numel))
 
 
 def pack_params(table_dev, n, dtype_code):

@@ -18,6 +18,12 @@ from . import lib as L_
 
 
 class FusedAdam(torch.optim.Optimizer):
+    # torch.amp.GradScaler protocol of fused optimizers: the scaler does NOT un-scale the gradients or read found_inf on the
+    # host; it hands `self.grad_scale` / `self.found_inf` (device scalars) to step(), and the kernel divides by the scale and
+    # skips the update on inf / nan itself (stgcma_adam_step_amp) -- no per-step host synchronisation in the caller's loop
+    # (traintest_adapt_ave29.py:165-168), which is what lets a launch-bound step run ahead / replay from CUDA graphs.
+    _step_supports_amp_scaling = True
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, maximize=False):
         if amsgrad or maximize:
             raise L_.StgcmaError("FusedAdam: amsgrad / maximize are not used by the STG-CMA callers and are not implemented")
@@ -27,6 +33,8 @@ class FusedAdam(torch.optim.Optimizer):
         if len(self.param_groups) > L_.ADAM_MAX_GROUPS:
             raise L_.StgcmaError(f"FusedAdam: at most {L_.ADAM_MAX_GROUPS} parameter groups")
         self._table, self._key, self._n, self._numel = None, None, 0, 0
+        self._skipped = None      # int32 device counter of steps skipped on inf / nan (GradScaler mode)
+        self._one = self._zero = None
 
     def _init_state(self):
         """exp_avg / exp_avg_sq of every parameter are views into two flat buffers (allocated once)."""
@@ -85,11 +93,45 @@ class FusedAdam(torch.optim.Optimizer):
             self._table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(active[0][1].device)
             self._key, self._n = key, len(active)
             self._numel = sum(p.numel() for _, p, _ in active)
-        groups = [None] * len(slots)
+        groups, steps = [None] * len(slots), [1] * len(slots)
         for (gi, t), slot in slots.items():
             g = self.param_groups[gi]
             b1, b2 = g["betas"]
             groups[slot] = dict(lr=g["lr"], weight_decay=g["weight_decay"], beta1=b1, beta2=b2, eps=g["eps"],
                                 bias_corr1=1.0 - b1 ** t, bias_corr2_sqrt=math.sqrt(1.0 - b2 ** t))
-        L_.adam_step(self._table, self._n, groups, grad_scale, numel=self._numel)
+            steps[slot] = t
+        amp_scale, found_inf = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
+        if isinstance(amp_scale, torch.Tensor) or isinstance(found_inf, torch.Tensor) or self._skipped is not None:
+            dev = active[0][1].device
+            if self._skipped is None:
+                self._skipped = torch.zeros(1, dtype=torch.int32, device=dev)
+                self._one, self._zero = torch.ones(1, device=dev), torch.zeros(1, device=dev)
+            sc = amp_scale if isinstance(amp_scale, torch.Tensor) else self._one
+            fi = found_inf if isinstance(found_inf, torch.Tensor) else self._zero
+            sc = sc.to(device=dev, dtype=torch.float32).reshape(1)
+            fi = fi.to(device=dev, dtype=torch.float32).reshape(1)
+            if grad_scale != 1.0:
+                sc = sc / grad_scale
+            L_.adam_step_amp(self._table, self._n, groups, steps, sc, fi, self._skipped, numel=self._numel)
+        else:
+            L_.adam_step(self._table, self._n, groups, grad_scale, numel=self._numel)
         return loss
+
+    def skipped_steps(self):
+        """Steps the GradScaler path skipped on inf / nan gradients (one host read)."""
+        return 0 if self._skipped is None else int(self._skipped.item())
+
+    def state_dict(self):
+        """`step` counts APPLIED updates, as torch.optim.Adam's does (the host counter also counts the skipped ones)."""
+        sd = super().state_dict()
+        k = self.skipped_steps()
+        if k:
+            for st in sd["state"].values():
+                if "step" in st:
+                    st["step"] = int(st["step"]) - k
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        if self._skipped is not None:
+            self._skipped.zero_()

@@ -550,6 +550,44 @@ def test_fused_adam_matches_torch_adam():
     assert rel(ours.state[our_p[0]]["exp_avg_sq"], ref.state[ref_p[0]]["exp_avg_sq"]) < 1e-6
 
 
+def test_fused_adam_under_gradscaler_matches_torch():
+    """torch.amp.GradScaler drives FusedAdam through the fused-optimizer protocol (`_step_supports_amp_scaling`): no
+    unscale pass, no host read of found_inf -- stgcma_adam_step_amp divides by the device-side scale, skips the update
+    when a gradient is inf and keeps the bias corrections on the count of APPLIED steps.  Against torch.optim.Adam under
+    its own GradScaler on the same scaled gradients, with an overflow injected in step 2 of 6."""
+    from stgcma.optim import FusedAdam
+    g = torch.Generator().manual_seed(1)
+    shapes = [(12, 96), (96,), (1,), (64, 128), (29, 512)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    kw = dict(weight_decay=5e-7, betas=(0.95, 0.999))
+    mk = lambda ps: [{"params": ps[:3], "lr": 5e-3}, {"params": ps[3:], "lr": 5e-4}]
+    ref, ours = torch.optim.Adam(mk(ref_p), **kw), FusedAdam(mk(our_p), **kw)
+    s_ref, s_our = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for sc in (s_ref, s_our):
+        sc.scale(torch.ones(1, device="cuda"))     # creates the device-side scale / growth tracker
+    for it in range(6):
+        scale = float(s_ref.get_scale())
+        assert float(s_our.get_scale()) == scale
+        for i, (a, b) in enumerate(zip(ref_p, our_p)):
+            gr = torch.randn(*shapes[i], generator=g).cuda() * scale       # what scaler.scale(loss).backward() leaves behind
+            if it == 2 and i == 3:
+                gr[5, 7] = float("inf")
+            a.grad, b.grad = gr.clone(), gr.clone()
+        for sc, opt in ((s_ref, ref), (s_our, ours)):
+            sc.step(opt)
+            sc.update()
+    torch.cuda.synchronize()
+    assert ours.skipped_steps() == 1
+    assert float(s_our.get_scale()) == float(s_ref.get_scale()) == 512.0      # halved once by the overflow
+    for a, b in zip(ref_p, our_p):
+        assert rel(b.detach(), a.detach()) < 1e-6
+    assert rel(ours.state[our_p[3]]["exp_avg_sq"], ref.state[ref_p[3]]["exp_avg_sq"]) < 1e-6
+    assert ours.state_dict()["state"][0]["step"] == 5 == int(ref.state_dict()["state"][0]["step"])
+    # the gradients are left un-scaled, like torch's fused Adam does
+    assert rel(our_p[0].grad, ref_p[0].grad) < 1e-6
+
+
 def test_fused_adam_load_state_dict_after_step():
     """load_state_dict() on a FusedAdam that has already stepped replaces the moment tensors (and a
     torch.optim.Adam checkpoint stores `step` as a tensor): the device table must follow, and the next step must equal
