@@ -24,6 +24,28 @@ constexpr int NP = 64;       // padded window length
 constexpr int NTH = 128;     // 4 warps
 constexpr float kScale = 0.17677669529663689f;  // 32^-0.5
 
+// Tiles hold N + 1 rows (N = ws * ws <= 49 tokens and one ZERO row): every fragment load clamps its row index to the zero
+// row instead of reading 64 padded rows -- 4 x 50 instead of 4 x 64 tile rows are what lets a fourth backward CTA (a sixth
+// forward CTA) fit an SM's shared memory.
+__device__ __forceinline__ void load_a_c(uint32_t (&a)[4], const uint8_t* tile, int ld, int row0, int k0, int lane, int rmax) {
+  int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  r = r < rmax ? r : rmax;
+  const int k = k0 + (lane >> 4) * 8;
+  ldsm_x4(a, smem_addr(tile + r * ld + k * 2));
+}
+__device__ __forceinline__ void load_b_nk_c(uint32_t (&b)[4], const uint8_t* tile, int ld, int n0, int k0, int lane, int rmax) {
+  int n = n0 + (lane & 7) + (lane >> 4) * 8;
+  n = n < rmax ? n : rmax;
+  const int k = k0 + ((lane >> 3) & 1) * 8;
+  ldsm_x4(b, smem_addr(tile + n * ld + k * 2));
+}
+__device__ __forceinline__ void load_b_kn_c(uint32_t (&b)[4], const uint8_t* tile, int ld, int k0, int n0, int lane, int rmax) {
+  int k = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  k = k < rmax ? k : rmax;
+  const int n = n0 + (lane >> 4) * 8;
+  ldsm_x4_t(b, smem_addr(tile + k * ld + n * 2));
+}
+
 struct Win {
   int16_t tok[NP];           // token row (within the frame) of window slot i
   int16_t rowoff[NP];        // yi * (2ws-1) + xi                         (0 for pad slots)
@@ -77,7 +99,7 @@ __device__ __forceinline__ void load_tbl(float* tbl, const float* __restrict__ r
 template <int HG>
 struct RowMap {
   static constexpr int CH = HG * 4, LD = HG * 64 + 16, RPP = NTH / CH, PASSES = (NP + RPP - 1) / RPP;
-  int tok[PASSES];   // token row of pass p, -1: pad row (zero fill), -2: beyond the tile / idle thread
+  int tok[PASSES];   // token row of pass p, -1: the zero row N (zero fill), -2: beyond the tile / idle thread
   int r0, c;
   __device__ __forceinline__ void init(const Win& w, int N, int tid) {
     r0 = tid / CH;
@@ -85,10 +107,10 @@ struct RowMap {
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
       const int r = r0 + p * RPP;
-      tok[p] = (r0 >= RPP || r >= NP) ? -2 : (r < N ? (int)w.tok[r] : -1);
+      tok[p] = (r0 >= RPP || r > N) ? -2 : (r < N ? (int)w.tok[r] : -1);   // row N: the zero row
     }
   }
-  // [N rows][HG*32] slice (column offset col0 of rows of `ld_g` elements) -> [NP][LD] tile; pad rows zero
+  // [N rows][HG*32] slice (column offset col0 of rows of `ld_g` elements) -> [N + 1][LD] tile; row N zero
   __device__ __forceinline__ void gather(uint8_t* tile, const bf16* __restrict__ src, int64_t frame_row0, int ld_g, int col0) const {
     const bf16* base = src + frame_row0 * ld_g + col0 + c * 8;
     uint8_t* dst = tile + r0 * LD + c * 16;
@@ -170,39 +192,40 @@ __device__ __forceinline__ void bias_mask(float (&s)[7][4], uint32_t pa, uint32_
 
 // write this lane's part of a 16 x 32 fp32 accumulator block (rows ra / rb of the tile, head h) as bf16 into a
 // [NP][LD] shared tile (the warp's own rows: conflict-free, see the LD padding)
-__device__ __forceinline__ void stage_rows(uint8_t* tile, int LD, const float (&o)[4][4], int ra, int rb, int h, int t) {
+__device__ __forceinline__ void stage_rows(uint8_t* tile, int LD, const float (&o)[4][4], int ra, int rb, int h, int t, int N) {
   uint8_t* pa = tile + ra * LD + (h * HD + 2 * t) * 2;
   uint8_t* pb = tile + rb * LD + (h * HD + 2 * t) * 2;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    *reinterpret_cast<uint32_t*>(pa + i * 16) = pack_bf16(o[i][0], o[i][1]);
-    *reinterpret_cast<uint32_t*>(pb + i * 16) = pack_bf16(o[i][2], o[i][3]);
+    if (ra < N) *reinterpret_cast<uint32_t*>(pa + i * 16) = pack_bf16(o[i][0], o[i][1]);
+    if (rb < N) *reinterpret_cast<uint32_t*>(pb + i * 16) = pack_bf16(o[i][2], o[i][3]);
   }
 }
 __device__ __forceinline__ void stage_rows(uint8_t* tile, int LD, const float (&o)[4][4], float sa, float sb, int ra, int rb,
-                                           int h, int t) {
+                                           int h, int t, int N) {
   uint8_t* pa = tile + ra * LD + (h * HD + 2 * t) * 2;
   uint8_t* pb = tile + rb * LD + (h * HD + 2 * t) * 2;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    *reinterpret_cast<uint32_t*>(pa + i * 16) = pack_bf16(o[i][0] * sa, o[i][1] * sa);
-    *reinterpret_cast<uint32_t*>(pb + i * 16) = pack_bf16(o[i][2] * sb, o[i][3] * sb);
+    if (ra < N) *reinterpret_cast<uint32_t*>(pa + i * 16) = pack_bf16(o[i][0] * sa, o[i][1] * sa);
+    if (rb < N) *reinterpret_cast<uint32_t*>(pb + i * 16) = pack_bf16(o[i][2] * sb, o[i][3] * sb);
   }
 }
 
 // 16 x 56 raw scores: A = 16 rows of `ta` (row block rb), B = rows of `tb` as [n][k]; features h*32 .. +31
-__device__ __forceinline__ void scores(float (&s)[7][4], const uint8_t* ta, const uint8_t* tb, int LD, int rb, int h, int lane) {
+__device__ __forceinline__ void scores(float (&s)[7][4], const uint8_t* ta, const uint8_t* tb, int LD, int rb, int h, int lane,
+                                       int N) {
 #pragma unroll
   for (int i = 0; i < 7; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
   uint32_t a[2][4];
-  load_a(a[0], ta, LD, rb * 16, h * HD, lane);
-  load_a(a[1], ta, LD, rb * 16, h * HD + 16, lane);
+  load_a_c(a[0], ta, LD, rb * 16, h * HD, lane, N);
+  load_a_c(a[1], ta, LD, rb * 16, h * HD + 16, lane, N);
 #pragma unroll
   for (int n2 = 0; n2 < 4; ++n2) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       uint32_t b[4];
-      load_b_nk(b, tb, LD, n2 * 16, h * HD + ks * 16, lane);
+      load_b_nk_c(b, tb, LD, n2 * 16, h * HD + ks * 16, lane, N);
       mma16816(s[2 * n2], a[ks], b[0], b[1]);
       if (n2 < 3) mma16816(s[2 * n2 + 1], a[ks], b[2], b[3]);
     }
@@ -222,27 +245,30 @@ __device__ __forceinline__ void pack_block(uint32_t (&pk)[16], const float (&p)[
 }
 
 // o[4 n-tiles of 32 features] += P (16 x 64 as packed A fragments) . tile[k][n]
-__device__ __forceinline__ void pv(float (&o)[4][4], const uint32_t (&pk)[16], const uint8_t* tv, int LD, int h, int lane) {
+__device__ __forceinline__ void pv(float (&o)[4][4], const uint32_t (&pk)[16], const uint8_t* tv, int LD, int h, int lane, int N) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     const uint32_t pa[4] = {pk[4 * kk], pk[4 * kk + 1], pk[4 * kk + 2], pk[4 * kk + 3]};
 #pragma unroll
     for (int n2 = 0; n2 < 2; ++n2) {
       uint32_t b[4];
-      load_b_kn(b, tv, LD, kk * 16, h * HD + n2 * 16, lane);
+      load_b_kn_c(b, tv, LD, kk * 16, h * HD + n2 * 16, lane, N);
       mma16816(o[2 * n2], pa, b[0], b[1]);
       mma16816(o[2 * n2 + 1], pa, b[2], b[3]);
     }
   }
 }
 
-// the packed 16 x 56 block of row block `rb` -> a [NP][LDP] bf16 shared tile (stmatrix: the accumulator layout IS the
-// 8 x 8 matrix fragment layout).  The tile holds 56 key columns; phase B's key block 48..63 reads columns 56..63 from the
-// next row (finite values of the same tile, one spare row allocated): they only feed discarded pad rows.
+// the packed 16 x 56 block of row block `rb` -> a [N + 2][LDP] bf16 shared tile (stmatrix: the accumulator layout IS the
+// 8 x 8 matrix fragment layout).  Rows <= N are kept (row N: a pad query, finite, contributes nothing because q and dO are
+// zero there); the other pad rows of the last row block all land on the dump row N + 1.  The tile holds 56 key columns; phase
+// B's key block 48..63 reads columns 56..63 from the next row (finite values of the same tile): they only feed discarded rows.
 constexpr int LDP = 112;   // 56 keys, 7 x 16 B: an odd chunk count keeps ldmatrix / stmatrix conflict-free
-__device__ __forceinline__ void store_block(uint8_t* tile, const uint32_t (&pk)[16], int rb, int lane) {
+__device__ __forceinline__ void store_block(uint8_t* tile, const uint32_t (&pk)[16], int rb, int lane, int N) {
   const int j = lane >> 3;
-  const uint32_t base = smem_addr(tile + (rb * 16 + (j & 1) * 8 + (lane & 7)) * LDP + (j >> 1) * 16);
+  int r = rb * 16 + (j & 1) * 8 + (lane & 7);
+  r = r <= N ? r : N + 1;
+  const uint32_t base = smem_addr(tile + r * LDP + (j >> 1) * 16);
 #pragma unroll
   for (int p = 0; p < 3; ++p)
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(base + p * 32), "r"(pk[4 * p]),
@@ -250,23 +276,25 @@ __device__ __forceinline__ void store_block(uint8_t* tile, const uint32_t (&pk)[
   asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1,%2};" ::"r"(base + 96), "r"(pk[12]), "r"(pk[13]) : "memory");
 }
 
-// A fragment (16 m x 16 k) of X^T where X is stored [k][m] row-major (row stride ld bytes)
-__device__ __forceinline__ void load_a_t(uint32_t (&a)[4], const uint8_t* tile, int ld, int m0, int k0, int lane) {
-  const int k = k0 + (lane & 7) + (lane >> 4) * 8;
+// A fragment (16 m x 16 k) of X^T where X is stored [k][m] row-major (row stride ld bytes); k rows clamped to rmax
+__device__ __forceinline__ void load_a_t(uint32_t (&a)[4], const uint8_t* tile, int ld, int m0, int k0, int lane, int rmax) {
+  int k = k0 + (lane & 7) + (lane >> 4) * 8;
+  k = k < rmax ? k : rmax;
   const int m = m0 + ((lane >> 3) & 1) * 8;
   ldsm_x4_t(a, smem_addr(tile + k * ld + m * 2));
 }
 
-// o[4 n-tiles of 32 features] += X^T (rows = columns rb*16.. of the [NP][LDP] tile sx, k = its 64 rows) . tile[k][n]
-__device__ __forceinline__ void xtv(float (&o)[4][4], const uint8_t* sx, const uint8_t* tile, int LD, int rb, int h, int lane) {
+// o[4 n-tiles of 32 features] += X^T (rows = columns rb*16.. of the [N + 2][LDP] tile sx, k = its query rows) . tile[k][n]
+__device__ __forceinline__ void xtv(float (&o)[4][4], const uint8_t* sx, const uint8_t* tile, int LD, int rb, int h, int lane,
+                                    int N) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     uint32_t a[4];
-    load_a_t(a, sx, LDP, rb * 16, kk * 16, lane);
+    load_a_t(a, sx, LDP, rb * 16, kk * 16, lane, N);
 #pragma unroll
     for (int n2 = 0; n2 < 2; ++n2) {
       uint32_t b[4];
-      load_b_kn(b, tile, LD, kk * 16, h * HD + n2 * 16, lane);
+      load_b_kn_c(b, tile, LD, kk * 16, h * HD + n2 * 16, lane, N);
       mma16816(o[2 * n2], a, b[0], b[1]);
       mma16816(o[2 * n2 + 1], a, b[2], b[3]);
     }
@@ -302,13 +330,14 @@ __global__ void __launch_bounds__(NTH) window_fwd_kernel(const bf16* __restrict_
                                                          bf16* __restrict__ out, int R, int ws, int shift, int heads) {
   constexpr int LD = HG * 64 + 16;
   extern __shared__ __align__(16) uint8_t wsm[];
+  const int N = ws * ws, NT = N + 1;                     // tile rows: N tokens + the zero row
   uint8_t* tq = wsm;
-  uint8_t* tk = tq + NP * LD;
-  uint8_t* tv = tk + NP * LD;
-  float* tbl = reinterpret_cast<float*>(tv + NP * LD);   // [HG][TS]
+  uint8_t* tk = tq + NT * LD;
+  uint8_t* tv = tk + NT * LD;
+  float* tbl = reinterpret_cast<float*>(tv + NT * LD);   // [HG][TS]
   const int TS = tbl_stride(ws), T2v = (2 * ws - 1) * (2 * ws - 1);
   Win& w = *reinterpret_cast<Win*>(tbl + HG * TS);
-  const int nwr = R / ws, nW = nwr * nwr, N = ws * ws, C = heads * HD, L = R * R;
+  const int nwr = R / ws, nW = nwr * nwr, C = heads * HD, L = R * R;
   const uint32_t ngrp = (uint32_t)(heads / HG);
   uint32_t b = blockIdx.x;                      // host checks frames * nW * ngrp < 2^31: 32-bit index math
   const int hg = (int)(b % ngrp); b /= ngrp;
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(NTH) window_fwd_kernel(const bf16* __restrict_
 #pragma unroll 1
   for (int h = 0; h < HG; ++h) {
     float s[7][4];
-    scores(s, tq, tk, LD, warp, h, lane);
+    scores(s, tq, tk, LD, warp, h, lane, N);
     if (masked) bias_mask<true>(s, pa0 + h * TS * 4, pb0 + h * TS * 4, ocb, ma, mb);
     else bias_mask<false>(s, pa0 + h * TS * 4, pb0 + h * TS * 4, ocb, ma, mb);
     float l0, l1;
@@ -349,10 +378,10 @@ __global__ void __launch_bounds__(NTH) window_fwd_kernel(const bf16* __restrict_
     float o[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    pv(o, pk, tv, LD, h, lane);
+    pv(o, pk, tv, LD, h, lane, N);
     // q rows of this warp / head are dead (only this warp read them): they stage the output
     __syncwarp();
-    stage_rows(tq, LD, o, 1.f / l0, 1.f / l1, ra, rb, h, t);
+    stage_rows(tq, LD, o, 1.f / l0, 1.f / l1, ra, rb, h, t, N);
   }
   __syncthreads();
   rm.scatter(tq, out, row0, C, hg * HG * HD);
@@ -363,21 +392,22 @@ __global__ void __launch_bounds__(NTH) window_fwd_kernel(const bf16* __restrict_
 // back by ldmatrix.trans -- nothing is recomputed.  Outputs are staged in the input tiles as their head slices die:
 // dq -> k, dk -> v (both dead after phase A of the head), dv -> dO (dead after phase B).
 template <int HG>
-__global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ rpb,
+__global__ void __launch_bounds__(NTH, 4) window_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ rpb,
                                                          const bf16* __restrict__ dout, bf16* __restrict__ dqkv, int R, int ws,
                                                          int shift, int heads) {
   constexpr int LD = HG * 64 + 16;
   extern __shared__ __align__(16) uint8_t wsm[];
+  const int N = ws * ws, NT = N + 1;                     // tile rows: N tokens + the zero row
   uint8_t* tq = wsm;
-  uint8_t* tk = tq + NP * LD;
-  uint8_t* tv = tk + NP * LD;
-  uint8_t* td = tv + NP * LD;
-  uint8_t* sp = td + NP * LD;                            // P  [NP queries][LDP]
-  uint8_t* sd = sp + (NP + 1) * LDP;                     // dS [NP queries][LDP]
-  float* tbl = reinterpret_cast<float*>(sd + (NP + 1) * LDP);  // [HG][TS]
+  uint8_t* tk = tq + NT * LD;
+  uint8_t* tv = tk + NT * LD;
+  uint8_t* td = tv + NT * LD;
+  uint8_t* sp = td + NT * LD;                            // P  [N + 2 queries][LDP]  (row N: pad query, row N + 1: dump)
+  uint8_t* sd = sp + (N + 2) * LDP;                      // dS [N + 2 queries][LDP]
+  float* tbl = reinterpret_cast<float*>(sd + (N + 2) * LDP);   // [HG][TS]
   const int TS = tbl_stride(ws), T2v = (2 * ws - 1) * (2 * ws - 1);
   Win& w = *reinterpret_cast<Win*>(tbl + HG * TS);
-  const int nwr = R / ws, nW = nwr * nwr, N = ws * ws, C = heads * HD, L = R * R;
+  const int nwr = R / ws, nW = nwr * nwr, C = heads * HD, L = R * R;
   const uint32_t ngrp = (uint32_t)(heads / HG);
   uint32_t b = blockIdx.x;                      // host checks frames * nW * ngrp < 2^31: 32-bit index math
   const int hg = (int)(b % ngrp); b /= ngrp;
@@ -412,13 +442,13 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
     {
       // ---------------- phase A: this warp's rows are queries ----------------
       float s[7][4], dp[7][4];
-      scores(s, tq, tk, LD, warp, h, lane);
+      scores(s, tq, tk, LD, warp, h, lane, N);
       if (masked) bias_mask<true>(s, pa0 + h * TS * 4, pb0 + h * TS * 4, ocb, ma, mb);
       else bias_mask<false>(s, pa0 + h * TS * 4, pb0 + h * TS * 4, ocb, ma, mb);
       float l0, l1;
       softmax_rows(s, l0, l1);
       const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-      scores(dp, td, tv, LD, warp, h, lane);   // dP = dO . v^T
+      scores(dp, td, tv, LD, warp, h, lane, N);   // dP = dO . v^T
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
@@ -435,15 +465,15 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
       }
       uint32_t pk[16];
       pack_block(pk, s);
-      store_block(sp, pk, warp, lane);
+      store_block(sp, pk, warp, lane, N);
       pack_block(pk, dp);
-      store_block(sd, pk, warp, lane);
+      store_block(sd, pk, warp, lane, N);
 #pragma unroll
       for (int i = 0; i < 4; ++i) oq[i][0] = oq[i][1] = oq[i][2] = oq[i][3] = 0.f;
-      pv(oq, pk, tk, LD, h, lane);             // dq = dS . k
+      pv(oq, pk, tk, LD, h, lane, N);             // dq = dS . k
     }
     __syncthreads();                           // P / dS complete; k and v slices of head h are dead
-    stage_rows(tk, LD, oq, ra, rb, h, t);
+    stage_rows(tk, LD, oq, ra, rb, h, t, N);
     // ---------------- phase B: this warp's rows are keys ----------------
     float ok[4][4], ov[4][4];
 #pragma unroll
@@ -451,11 +481,11 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
       ok[i][0] = ok[i][1] = ok[i][2] = ok[i][3] = 0.f;
       ov[i][0] = ov[i][1] = ov[i][2] = ov[i][3] = 0.f;
     }
-    xtv(ok, sd, tq, LD, warp, h, lane);        // dk = dS^T . q
-    xtv(ov, sp, td, LD, warp, h, lane);        // dv = P^T . dO
-    stage_rows(tv, LD, ok, ra, rb, h, t);
+    xtv(ok, sd, tq, LD, warp, h, lane, N);        // dk = dS^T . q
+    xtv(ov, sp, td, LD, warp, h, lane, N);        // dv = P^T . dO
+    stage_rows(tv, LD, ok, ra, rb, h, t, N);
     __syncthreads();                           // q and dO slices of head h are dead; P / dS may be overwritten
-    stage_rows(td, LD, ov, ra, rb, h, t);
+    stage_rows(td, LD, ov, ra, rb, h, t, N);
   }
   __syncthreads();
   rm.scatter(tk, dqkv, row0, 3 * C, hg * HG * HD);
@@ -466,7 +496,7 @@ __global__ void __launch_bounds__(NTH) window_bwd_kernel(const bf16* __restrict_
 static int pick_hg(int heads) {
   static const int force = getenv("STGCMA_WIN_HG") ? atoi(getenv("STGCMA_WIN_HG")) : 0;   // tuning knob
   if (force > 0 && heads % force == 0) return force;
-  if (heads % 3 == 0) return 3;   // backward: 4 tiles + P / dS = 74 KB -> 3 CTAs per SM
+  if (heads % 3 == 0) return 3;   // backward: 4 tiles of 50 rows + P / dS = 55 KB -> 4 CTAs per SM
   if (heads % 2 == 0) return 2;
   return 1;
 }
@@ -475,7 +505,7 @@ template <int HG>
 static int fwd_launch(const void* qkv, const float* rpb, void* out, int64_t frames, int R, int ws, int shift, int heads,
                       cudaStream_t st) {
   constexpr int LD = HG * 64 + 16;
-  const size_t smem = (size_t)3 * NP * LD + sizeof(float) * HG * tbl_stride(ws) + sizeof(Win);
+  const size_t smem = (size_t)3 * (ws * ws + 1) * LD + sizeof(float) * HG * tbl_stride(ws) + sizeof(Win);
   auto kern = window_fwd_kernel<HG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("window_attn_fwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
@@ -488,7 +518,7 @@ template <int HG>
 static int bwd_launch(const void* qkv, const float* rpb, const void* dout, void* dqkv, int64_t frames, int R, int ws, int shift,
                       int heads, cudaStream_t st) {
   constexpr int LD = HG * 64 + 16;
-  const size_t smem = (size_t)4 * NP * LD + (size_t)2 * (NP + 1) * LDP + sizeof(float) * HG * tbl_stride(ws) + sizeof(Win);
+  const size_t smem = (size_t)4 * (ws * ws + 1) * LD + (size_t)2 * (ws * ws + 2) * LDP + sizeof(float) * HG * tbl_stride(ws) + sizeof(Win);
   auto kern = window_bwd_kernel<HG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("window_attn_bwd(tc): smem attr: %s", cudaGetErrorString(e)); return STGCMA_ECUDA; }
