@@ -512,6 +512,10 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   // either the whole N fits one tile or the tile width is a multiple of 64 (and <= 128: two staging blocks).
   // (Forcing BN = 128 for N = 288 to qualify was slower than BN = 96 with the transposing epilogue: measured.)
   const bool tma_cand = ep.mode == STGCMA_EPI_LINEAR && !ep.out_f32 && !ep.res1 && !ep.res2 && !ep.rowscale;
+  // two CTAs per SM, plain output, several n-tiles: a tile width of 64 / 128 keeps the TMA-store epilogue (~2 instructions per
+  // element) where the padding-optimal width (e.g. 96 for N = 192 / 576) would fall back to the transposing one (~17)
+  static const int tma64 = getenv("STGCMA_GEMM_TMA64") ? atoi(getenv("STGCMA_GEMM_TMA64")) : 1;
+  if (tma64 && occ == 2 && tma_cand && N > 128 && N % 64 == 0 && best_bn % 64 != 0) best_bn = (N % 128 == 0) ? 128 : 64;
   p.BN = best_bn;
   p.n_tiles = (int)ceil_div(N, p.BN);
   p.m_tiles_g = (int)ceil_div(p.group_rows, BM);
