@@ -32,6 +32,8 @@ CASES = [
     # the configuration the authors publish (run_adapt_ave29.py:156-165) at FULL depth [2, 2, 18, 2]: heads 4 / 8 / 16 / 32
     # (window attention in head groups of 2), r = 16 / 32 / 32 / 64, C = 128 .. 1024
     ("swin_b_T2_B1_fusion", dict(img_size=224, num_frames=2, label_dim=29, **O.PRESETS["swin_b"]), 1, "fusion"),
+    # run_adapt_ave29.py:171-181 at full depth: C = 192 .. 1536, heads 6 .. 48, r = 96 at every stage (ratios .5 / .25 / .125 / .0625)
+    ("swin_l_T2_B1_fusion", dict(img_size=224, num_frames=2, label_dim=29, **O.PRESETS["swin_l"]), 1, "fusion"),
 ]
 # every case uses bf16-representable weights (make_state docstring): the same fixture then serves the fp32
 # check mode (1e-3) and the bf16 production mode (2e-2) with IDENTICAL weights on both sides

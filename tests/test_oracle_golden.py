@@ -11,7 +11,7 @@ from oracle.make_goldens import probe_index
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion", "swin_t_T10_B2_fusion", "swin_b_T2_B1_fusion"])
+@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion", "swin_t_T10_B2_fusion", "swin_b_T2_B1_fusion", "swin_l_T2_B1_fusion"])
 def test_oracle_reproduces_reference(name):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     cfg = O.SwinAVEConfig(**fx["cfg"])

@@ -126,7 +126,7 @@ def test_other_presets_step_vs_oracle(preset, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion", "swin_t_T10_B2_fusion", "swin_b_T2_B1_fusion"])
+@pytest.mark.parametrize("name", ["tiny3stage_fusion", "tiny3stage_multimodal", "swin_t_T2_fusion", "swin_t_T10_B2_fusion", "swin_b_T2_B1_fusion", "swin_l_T2_B1_fusion"])
 def test_step_vs_reference_golden(name, dtype):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     cfg = O.SwinAVEConfig(**fx["cfg"])
