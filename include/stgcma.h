@@ -236,6 +236,24 @@ int stgcma_adam_step(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGr
  * un-scaled; when *found_inf_dev != 0 nothing is updated and *skipped_dev (int32, cumulative) is incremented, so the
  * bias corrections -- computed in the kernel from steps_host[group] - *skipped_dev -- do not advance either.
  * groups_host->bias_corr1 / bias_corr2_sqrt are ignored.                                                           */
+/* ---- data-parallel exchange: mean of the flat gradient bucket over the GPUs of one box --------------
+ * Replaces the caller's nn.DataParallel reduce / an NCCL all-reduce of the adapter + head gradients
+ * (traintest_adapt_ave29.py:32-33): every rank's bucket lives in symmetric (peer-mapped) memory; each rank reads the W
+ * buckets over NVLink / NVSwitch with 128-bit loads and writes  out[i] = scale * sum_r peer[r][i]  into its own local
+ * tensor -- a one-shot all-reduce (8.9 MB for Swin-T: latency bound, one launch, no staging copies).  `peers_dev` is a
+ * DEVICE array of `world` pointers to the ranks' buckets (this rank's own included), all 16-byte aligned; n floats.
+ * `mc` (nullable): the NVLS multicast address of the same symmetric allocation; when given, the sum is taken by the
+ * switch (multimem.ld_reduce) and `peers_dev` is not read.  The caller brackets the launch with cross-rank barriers
+ * (the buckets must be complete before, and must not be rewritten until every rank has read them).                   */
+int stgcma_bucket_allreduce(const float* const* peers_dev, int world, const float* mc, float* out, int64_t n, float scale,
+                            void* stream);
+
+/* Two-shot variant for larger boxes (the one-shot reads W buckets per rank): rank r reduces ONLY its slice
+ * [r n / W, (r + 1) n / W) of the bucket through the switch (multimem.ld_reduce on `mc_in`) and broadcasts the scaled result
+ * into every rank's copy of a second symmetric buffer with multimem.st on `mc_out` -- n / W elements per rank instead of n.
+ * Barriers by the caller before (buckets complete) and after (every slice has landed everywhere).  n % (4 world) == 0.  */
+int stgcma_bucket_allreduce_nvls(const float* mc_in, float* mc_out, int64_t n, int rank, int world, float scale, void* stream);
+
 int stgcma_adam_step_amp(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host,
                          const int32_t* steps_host /* [STGCMA_ADAM_MAX_GROUPS] */, const float* scale_dev,
                          const float* found_inf_dev, int32_t* skipped_dev, void* stream);

@@ -545,6 +545,67 @@ __global__ void __launch_bounds__(256) adam_kernel(const StgcmaAdamEntry* __rest
   }
 }
 
+// =========================================================================================
+// One-shot all-reduce of the gradient bucket over peer-mapped (symmetric) memory
+// =========================================================================================
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { const float* p[kMaxPeers]; };
+
+__global__ void __launch_bounds__(256) bucket_allreduce_kernel(const float* const* __restrict__ peers_dev, int world,
+                                                               float* __restrict__ out, int64_t n4, int64_t n, float scale) {
+  __shared__ const float* sp[kMaxPeers];
+  if (threadIdx.x < world) sp[threadIdx.x] = peers_dev[threadIdx.x];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < world; ++r) {
+      // peer memory is written by other GPUs: volatile-strength loads that bypass L1 (the barrier before the launch orders them)
+      float4 v;
+      asm volatile("ld.global.relaxed.sys.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "l"(reinterpret_cast<const float4*>(sp[r]) + i));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+  }
+  // tail (n % 4 floats)
+  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float a = 0.f;
+    for (int r = 0; r < world; ++r) {
+      float v;
+      asm volatile("ld.global.relaxed.sys.f32 %0, [%1];" : "=f"(v) : "l"(sp[r] + i));
+      a += v;
+    }
+    out[i] = a * scale;
+  }
+}
+
+// NVLS: the switch adds the W copies (multimem.ld_reduce on the multicast mapping of the symmetric allocation)
+__global__ void __launch_bounds__(256) bucket_allreduce_mc_kernel(const float* __restrict__ mc, float* __restrict__ out,
+                                                                  int64_t n4, float scale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<const float4*>(mc) + i) : "memory");
+    reinterpret_cast<float4*>(out)[i] = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+  }
+}
+
+// two-shot NVLS: reduce the rank's slice in the switch, broadcast it to every rank's output copy
+__global__ void __launch_bounds__(256) bucket_allreduce_nvls_kernel(const float* __restrict__ mc_in, float* __restrict__ mc_out,
+                                                                    int64_t lo4, int64_t hi4, float scale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<const float4*>(mc_in) + i) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<float4*>(mc_out) + i),
+                 "f"(v.x * scale), "f"(v.y * scale), "f"(v.z * scale), "f"(v.w * scale) : "memory");
+  }
+}
+
 // GradScaler variant: scale / found_inf are device scalars, bias corrections from the device-side count of applied steps
 struct AdamSteps { int32_t t[STGCMA_ADAM_MAX_GROUPS]; };
 __global__ void __launch_bounds__(256) adam_amp_kernel(const StgcmaAdamEntry* __restrict__ table, const StgcmaAdamGroups hp,
@@ -588,6 +649,41 @@ __global__ void __launch_bounds__(256) adam_amp_kernel(const StgcmaAdamEntry* __
 }  // namespace stgcma
 
 using namespace stgcma;
+
+extern "C" int stgcma_bucket_allreduce(const float* const* peers_dev, int world, const float* mc, float* out, int64_t n,
+                                       float scale, void* stream) {
+  STG_REQUIRE(out && n > 0 && world >= 1 && world <= kMaxPeers, "bucket_allreduce: bad arguments (world=%d)", world);
+  STG_REQUIRE(mc || peers_dev, "bucket_allreduce: no source");
+  STG_REQUIRE(((uintptr_t)out & 15) == 0, "bucket_allreduce: out must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (mc) {
+    STG_REQUIRE(n % 4 == 0 && ((uintptr_t)mc & 15) == 0, "bucket_allreduce: the multicast path needs n %% 4 == 0");
+    bucket_allreduce_mc_kernel<<<(unsigned)blocks, 256, 0, st>>>(mc, out, n4, scale);
+  } else {
+    bucket_allreduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(peers_dev, world, out, n4, n, scale);
+  }
+  return check_launch("bucket_allreduce");
+}
+
+extern "C" int stgcma_bucket_allreduce_nvls(const float* mc_in, float* mc_out, int64_t n, int rank, int world, float scale,
+                                            void* stream) {
+  STG_REQUIRE(mc_in && mc_out && n > 0 && world >= 1 && rank >= 0 && rank < world, "bucket_allreduce_nvls: bad arguments");
+  STG_REQUIRE(n % (4 * (int64_t)world) == 0, "bucket_allreduce_nvls: n=%lld must be a multiple of 4 * world", (long long)n);
+  STG_REQUIRE((((uintptr_t)mc_in | (uintptr_t)mc_out) & 15) == 0, "bucket_allreduce_nvls: 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t per4 = n / 4 / world, lo4 = per4 * rank, hi4 = lo4 + per4;
+  int64_t blocks = (per4 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  bucket_allreduce_nvls_kernel<<<(unsigned)blocks, 256, 0, st>>>(mc_in, mc_out, lo4, hi4, scale);
+  return check_launch("bucket_allreduce_nvls");
+}
 
 extern "C" int stgcma_adam_step_amp(const StgcmaAdamEntry* table_dev, int n, const StgcmaAdamGroups* groups_host,
                                     const int32_t* steps_host, const float* scale_dev, const float* found_inf_dev,

@@ -19,7 +19,7 @@ import os
 import torch
 
 from . import lib as L_
-from .engine import _Arena, _StepGraphs, _rup, _EPS_PAD
+from .engine import _Arena, _DpExchange, _StepGraphs, _rup, _EPS_PAD
 
 
 class ClipAVEEngine:
@@ -32,7 +32,7 @@ class ClipAVEEngine:
         self.train_pack = None
         self.train_key = None
         self.generation = 0
-        self.dp_allreduce = True
+        self.dp = _DpExchange()       # mean of the gradient bucket over the ranks (peer-memory all-reduce; engine._DpExchange)
         self.side_stream_dw = os.environ.get("STGCMA_SIDE_DW", "1") != "0"
         self._side = {}
         self.graphs = _StepGraphs()   # CUDA-graph replay of the schedules for launch-bound steps (engine._StepGraphs)
@@ -40,6 +40,14 @@ class ClipAVEEngine:
     @property
     def arena(self):
         return self.arena_
+
+    @property
+    def dp_allreduce(self):
+        return self.dp.enabled
+
+    @dp_allreduce.setter
+    def dp_allreduce(self, v):
+        self.dp.enabled = bool(v)
 
     @property
     def graph_mode(self):
@@ -394,17 +402,19 @@ class ClipAVEEngine:
                                  "(run forward -> backward -> forward ...)")
         dev = sv["dev"]
         pk = self.train_pack
-        gbuf = self.arena_.get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
+        gbuf = self.dp.bucket(pk["_gsize"], dev)
+        if gbuf is None:
+            gbuf = self.arena_.get("grad_bucket", (pk["_gsize"],), torch.float32, dev)
+        out = None
         if sv.get("graph") is not None:
             out = self.graphs.backward(sv["graph"], dlogits, gbuf, self._backward_part)
         else:
             gbuf.zero_()
             self._backward_part(sv, dlogits, gbuf)
+        if self.dp.active():
+            out = self.dp.reduce(gbuf)
+        elif out is None:
             out = gbuf.clone()
-        if self.dp_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(out)
-            out.div_(torch.distributed.get_world_size())
         goffs = pk["_goffs"]
         grads = []
         for name, prm in self.trainable_params():

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "stgcma_pack_params": [_vp, _i, _i, _vp],
     "stgcma_adam_step": [_vp, _i, _vp, ctypes.c_float, _vp],
     "stgcma_adam_step_amp": [_vp, _i, _vp, _vp, _fp, _fp, _vp, _vp],
+    "stgcma_bucket_allreduce": [_vp, _i, _fp, _fp, _i64, ctypes.c_float, _vp],
+    "stgcma_bucket_allreduce_nvls": [_fp, _fp, _i64, _i, _i, ctypes.c_float, _vp],
     "stgcma_mha_fwd": [_vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_mha_bwd": [_vp, _vp, _fp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _vp],
     "stgcma_im2col": [_fp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i, _vp],
@@ -385,6 +387,19 @@ def adam_step_amp(table_dev, n, groups, steps, scale_dev, found_inf_dev, skipped
     st = (ctypes.c_int32 * ADAM_MAX_GROUPS)(*([int(t) for t in steps] + [1] * (ADAM_MAX_GROUPS - len(steps))))
     _call("stgcma_adam_step_amp", _p(table_dev), n, ctypes.cast(hp, ctypes.c_void_p), ctypes.cast(st, ctypes.c_void_p),
           _p(scale_dev), _p(found_inf_dev), _p(skipped_dev), cost=(0.0, 32.0 * numel))
+
+
+def bucket_allreduce(peers_dev_ptr, world, out, n, scale, mc_ptr=None):
+    """out[i] = scale * sum over the ranks' symmetric buckets (device array of `world` pointers at `peers_dev_ptr`, or the NVLS
+    multicast address `mc_ptr`); the caller brackets the launch with cross-rank barriers."""
+    require_device(out)
+    _call("stgcma_bucket_allreduce", peers_dev_ptr, world, mc_ptr, _p(out), n, ctypes.c_float(scale),
+          cost=(0.0, 4.0 * n * (world + 1)))
+
+
+def bucket_allreduce_nvls(mc_in_ptr, mc_out_ptr, n, rank, world, scale):
+    """Two-shot NVLS all-reduce: this rank reduces its 1 / world slice in the switch and multicasts it to every rank's output."""
+    _call("stgcma_bucket_allreduce_nvls", mc_in_ptr, mc_out_ptr, n, rank, world, ctypes.c_float(scale), cost=(0.0, 8.0 * n / world))
 
 
 def pack_params(table_dev, n, dtype_code):
