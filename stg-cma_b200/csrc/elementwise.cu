@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   const int K = Cin * 16;
   float* wt = smem;                 // [K][C]
   float* sb = wt + K * C;           // bias, gamma, beta: [3][C]
-  float* sin = sb + 3 * C;          // [Cin*4][W]
+  float* sin0 = sb + 3 * C;         // 2 x [Cin*4][W]: the next strip is copied in (cp.async) while this one is computed
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   for (int i = tid; i < K * C; i += blockDim.x) {
     const int c = i / K, k = i - c * K;  // w is [C][K]
@@ -391,16 +391,36 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
   }
   const int Hp = H >> 2, Wp = W >> 2;
   const int64_t nstrips = (int64_t)B * Tn * Hp;
-  for (int64_t strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+  const int W4 = W >> 2, nvec = Cin * 4 * W4;      // 16-byte chunks of a strip (W % 4 == 0, img 16-byte aligned: host checks)
+  // The strip copy used to be a scalar global -> shared loop with a division per element and its load latency exposed
+  // once per strip (10 dependent round trips: 3/4 of the kernel's time, 0.19 of the HBM roof); now 16-byte cp.async into the
+  // other half of a double buffer, issued one strip ahead.
+  auto copy_strip = [&](int64_t strip, float* dst) {
     const int y = (int)(strip % Hp);
-    const int64_t f = strip / Hp;  // frame index b*T + t
+    const int64_t f = strip / Hp;
     const int t = (int)(f % Tn);
     const int b = (int)(f / Tn);
-    __syncthreads();
-    for (int i = tid; i < Cin * 4 * W; i += blockDim.x) {
-      const int rowi = i / W, xx = i - rowi * W;
+    for (int i = tid; i < nvec; i += blockDim.x) {
+      const int rowi = i / W4, x4 = i - rowi * W4;
       const int ci = rowi >> 2, ky = rowi & 3;
-      sin[i] = img[((((int64_t)b * Cin + ci) * Tn + t) * H + (4 * y + ky)) * W + xx];
+      const float* src = img + ((((int64_t)b * Cin + ci) * Tn + t) * H + (4 * y + ky)) * W + 4 * x4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + rowi * W + 4 * x4)),
+                   "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if ((int64_t)blockIdx.x < nstrips) copy_strip(blockIdx.x, sin0);
+  for (int64_t strip = blockIdx.x; strip < nstrips; strip += gridDim.x, buf ^= 1) {
+    const int y = (int)(strip % Hp);
+    const int64_t f = strip / Hp;  // frame index b*T + t
+    const float* sin = sin0 + buf * (Cin * 4 * W);
+    __syncthreads();               // every warp is done with the buffer the next copy overwrites (and wt / sb are loaded)
+    if (strip + gridDim.x < nstrips) {
+      copy_strip(strip + gridDim.x, sin0 + (buf ^ 1) * (Cin * 4 * W));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     // Register tile: a warp owns TT tokens (x = warp + nwarp * i) x `per` channels per lane, so that every staged
@@ -755,7 +775,7 @@ extern "C" int stgcma_patch_embed_fwd(const float* img, const float* w, const fl
   STG_REQUIRE(C % 32 == 0 && C <= 256, "patch_embed_fwd: C=%d must be a multiple of 32 and <= 256", C);
   STG_REQUIRE(Cin >= 1 && Cin <= 4, "patch_embed_fwd: Cin=%d unsupported", Cin);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = sizeof(float) * ((size_t)Cin * 16 * C + 3 * C + (size_t)Cin * 4 * W);
+  const size_t smem = sizeof(float) * ((size_t)Cin * 16 * C + 3 * C + (size_t)2 * Cin * 4 * W);   // weights + 2 strip buffers
   const int64_t strips = (int64_t)B * T * (H / 4);
   const int grid = (int)(strips < (int64_t)sm_count() * 4 ? strips : (int64_t)sm_count() * 4);
   STG_REQUIRE(W % 4 == 0 && ((uintptr_t)img & 15) == 0, "patch_embed_fwd: img must be 16-byte aligned");
