@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(NW * 32) xg_fwd_kernel(const bf16* __restrict_
 // backward
 // ---------------------------------------------------------------------------------------------
 template <int RP, int NW>
-__global__ void __launch_bounds__(NW * 32) xg_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ hpre,
+__global__ void __launch_bounds__(NW * 32, (RP <= 16 ? 8 : 0)) xg_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ hpre,
                                                          const float* __restrict__ gate, const float* __restrict__ lse,
                                                          const float* __restrict__ D, const bf16* __restrict__ dout,
                                                          bf16* __restrict__ dh, int64_t frames, int L, int La) {

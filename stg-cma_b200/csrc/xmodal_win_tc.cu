@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) xw_fwd_kernel(const bf16* __restrict__ h,
 
 // ---------------------------------------------------------------------------------------------
 template <int RP>
-__global__ void __launch_bounds__(256, (RP <= 16 ? 4 : RP <= 32 ? 3 : 1)) xw_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ hpre,
+__global__ void __launch_bounds__(256, (RP <= 16 ? 4 : RP <= 32 ? 3 : 0)) xw_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ hpre,
                                                      const float* __restrict__ gate, const bf16* __restrict__ attn_out,
                                                      const bf16* __restrict__ dout, bf16* __restrict__ dh,
                                                      float* __restrict__ dgate, int64_t frames, int R, int ws, int shift) {
