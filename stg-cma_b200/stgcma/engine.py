@@ -143,6 +143,7 @@ class _StepGraphs:
     def __init__(self):
         self.mode = os.environ.get("STGCMA_GRAPH", "auto")
         self.max_clips = 8
+        self.max_entries = 6         # captured (mode, shape, flags) keys kept alive; each holds its graphs' private pool
         self.entries = {}
 
     def wanted(self, B, dev):
@@ -152,10 +153,13 @@ class _StepGraphs:
 
     def forward(self, key, fz, pk, a32, v32, run):
         """run(a, v) -> (logits, part) launches the forward schedule.  Returns (logits, part, entry or None)."""
-        ent = self.entries.get(key)
+        ent = self.entries.pop(key, None)
         if ent is None or ent["fz"] is not fz or ent["pk"] is not pk:
             # (new weight caches invalidate the captured addresses: start over)
-            ent = self.entries[key] = dict(fz=fz, pk=pk, seen=0, fwd=None, bwd=None)
+            ent = dict(fz=fz, pk=pk, seen=0, fwd=None, bwd=None)
+        self.entries[key] = ent                 # most recently used last
+        while len(self.entries) > self.max_entries:
+            self.entries.pop(next(iter(self.entries)))   # e.g. the odd last batch of every epoch: drop the oldest capture
         if ent["seen"] < 2:
             ent["seen"] += 1
             logits, part = run(a32, v32)
