@@ -620,3 +620,18 @@ def test_fused_adam_load_state_dict_after_step():
     torch.cuda.synchronize()
     for p, q in zip(pa, pb):
         assert rel(p.detach(), q.detach()) < 1e-6
+
+
+def test_bucket_allreduce_single_gpu_mechanics():
+    """stgcma_bucket_allreduce on ONE GPU: the 'peers' are three local buffers (the kernel only sees a device array of
+    pointers), so out = scale * (b0 + b1 + b2) including the n % 4 tail.  The real exchange over peer-mapped memory and
+    the NVLS kernels run under torchrun: scripts/dp_exchange_check.py (2 and 8 GPUs, profiles/r02d_dp_exchange_n8.txt)."""
+    n = 100003
+    bufs = [rnd(n, dtype=torch.float32, seed=40 + i) for i in range(3)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    out = torch.full((n,), float("nan"), device="cuda")
+    L().bucket_allreduce(ptrs.data_ptr(), 3, out, n, 1.0 / 3.0)
+    ref = (bufs[0].double() + bufs[1].double() + bufs[2].double()) / 3.0
+    assert rel(out, ref) < 1e-6
+    with pytest.raises(L().StgcmaError):
+        L().bucket_allreduce(ptrs.data_ptr(), 17, out, n, 1.0)     # more peers than the kernel supports

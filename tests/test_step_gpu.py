@@ -370,3 +370,24 @@ def test_cuda_graph_replay_draws_fresh_drop_path_masks():
         parts.append(m.mlp_head[2].weight.grad.clone())
     assert rel(parts[1] - parts[0], parts[0]) > 1e-3   # the second pass added something (different masks: not exactly 2x)
     assert torch.isfinite(parts[1]).all()
+
+
+def test_cuda_graph_cache_is_bounded():
+    """Every (mode, shape, flags) key holds captured graphs and their private memory pool: the cache keeps the most recently
+    used keys only (the odd last batch of an epoch must not pin memory forever), and an evicted key simply warms up again."""
+    cfg = O.SwinAVEConfig(**TINY)
+    sd = O.make_state(cfg, seed=9)
+    m = build(TINY, "fusion", torch.float32, sd)
+    eng = m.engine()
+    eng.graph_mode = "1"
+    eng.graphs.max_entries = 2
+    ref = {}
+    for rounds in range(2):
+        for B in (1, 2, 3):
+            a, v, labels = O.make_inputs(cfg, B, seed=20 + B)
+            for it in range(3):                   # third call of a key replays its graphs
+                out, _, g = step(m, a, v, labels, "fusion")
+            assert len(eng._graphs) <= 2
+            if B in ref:
+                assert rel(out, ref[B][0]) < 1e-5 and rel(g["mlp_head.2.weight"], ref[B][1]) < 1e-5
+            ref[B] = (out, g["mlp_head.2.weight"])
