@@ -65,8 +65,9 @@ class _DpExchange:
     On a CUDA box the bucket lives in symmetric (peer-mapped) memory (`torch.distributed._symmetric_memory`): the weight-gradient
     kernels accumulate straight into it, and `stgcma_bucket_allreduce` -- one launch between two cross-rank barriers -- reads the
     W buckets over NVLink / NVSwitch and writes the mean into a local tensor (8.9 MB for Swin-T: a latency-bound one-shot
-    all-reduce, no NCCL call, no staging copy; 38 us against NCCL's 58 us on 2 GPUs).  Above 4 ranks reading W whole buckets
-    per rank loses to a reduce-scatter / all-gather shape, so the default ("auto") switches to the two-shot NVLS kernel when
+    all-reduce, no NCCL call, no staging copy; 38 us against NCCL's 58 us on 2 GPUs).  From 4 ranks on, reading W whole buckets
+    per rank loses to a reduce-scatter / all-gather shape (4 GPUs: 74 us one-shot, 64 us two-shot, NCCL 93 us; 8 GPUs: 177 / 54 /
+    85 us), so the default ("auto") switches to the two-shot NVLS kernel when
     the box has NVSwitch multicast: each rank reduces 1 / W of the bucket IN THE SWITCH (multimem.ld_reduce) and multicasts the
     result into every rank's output copy (multimem.st).  STGCMA_DP=peer | nvls1 (one-shot through the switch) | nvls | nccl
     force a mode; `torch.distributed.all_reduce` is also what runs when symmetric memory cannot be set up (logged once) and on
@@ -113,7 +114,7 @@ class _DpExchange:
         W = self.world()
         if self.hdl is not None and gbuf is self.t:
             npad = self.full.numel()
-            two_shot = self.ohdl is not None and (self.mode == "nvls" or (self.mode == "auto" and W > 4))
+            two_shot = self.ohdl is not None and (self.mode == "nvls" or (self.mode == "auto" and W >= 4))
             self.hdl.barrier(channel=0)       # every rank's bucket is complete
             if two_shot:
                 L_.bucket_allreduce_nvls(self.hdl.multicast_ptr, self.ohdl.multicast_ptr, npad, self.hdl.rank, W, 1.0 / W)
