@@ -40,6 +40,21 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return x * fmaf(0.5f, th, 0.5f);
 }
 
+// Activation AND derivative from the tanh form: Phi as in gelu_tanh (|error| <= 2.4e-4), the Gaussian term of the derivative
+// from one ex2 -- 12 issue slots (2 MUFU) instead of the ~30 of the erf / expf / rcp form (ncu, profiles/r02d_ncu_gemm_fc1g_s2.txt:
+// the derivative-saving fc1 GEMMs of stages 2-3 spend 3/4 of their epilogue instructions there).  Both results are rounded to
+// bf16 (2^-9 relative) right after.
+__device__ __forceinline__ void gelu_val_grad_tanh(float x, float& y, float& dy) {
+  const float t = fminf(x * x, 80.0f);
+  const float g = x * fmaf(t, fmaf(t, -3.51519793e-04f, 3.70056659e-02f), 7.97507861e-01f);
+  float th, e;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(g));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * -0.72134752044448170f));   // exp(-x^2 / 2)
+  const float cdf = fmaf(0.5f, th, 0.5f);
+  y = x * cdf;
+  dy = fmaf(x * 0.39894228040143268f, e, cdf);
+}
+
 __device__ __forceinline__ float gelu_grad_poly(float x) {
   const float xc = fminf(fmaxf(x, -4.5f), 4.5f);
   const float t = xc * xc;

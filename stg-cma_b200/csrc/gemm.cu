@@ -11,6 +11,7 @@
 //                    fp32 atomics into the gradient bucket.
 #include <stdlib.h>
 #include "tc_common.cuh"
+#include "gelu_poly.cuh"
 
 namespace stgcma {
 
@@ -57,6 +58,15 @@ __device__ __forceinline__ void epi_elem(const EpiParams& p, int64_t row, int co
       st_f(out + off, v * a);
     } break;
   }
+}
+
+// GELU + GELU' of the derivative-saving epilogue: the tanh form by default (STGCMA_GELU_ERF=1 at compile time keeps the erf form)
+__device__ __forceinline__ void gelu_val_grad_act(float x, float& y, float& dy) {
+#ifdef STGCMA_GELU_ERF
+  gelu_val_grad_fast(x, y, dy);
+#else
+  gelu_val_grad_tanh(x, y, dy);
+#endif
 }
 
 // Epilogue of the tcgen05 kernel.  An epilogue warp owns 32 rows x 32 columns per step.  The 32x32b TMEM load
@@ -136,7 +146,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int64_t off, int p
     float d[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (MODE == STGCMA_EPI_GELU_G) gelu_val_grad_fast(v[i], v[i], d[i]);
+      if (MODE == STGCMA_EPI_GELU_G) gelu_val_grad_act(v[i], v[i], d[i]);
       else qgelu_val_grad(v[i], v[i], d[i]);
     }
     if (p.out_pre) store8(reinterpret_cast<bf16*>(p.out_pre) + off, d);
@@ -230,10 +240,12 @@ struct Params {
 // OCC: CTAs per SM the variant is compiled for.  OCC = 2 (BN <= 128, half the smem / TMEM each) is used for the
 // small-K, epilogue-bound shapes: two tiles in flight per SM hide the epilogue latency; OCC = 1 (BN <= 256) for the
 // large-K, tensor-bound ones (a 128 x 256 tile reads 25 % less shared memory per flop than two 128 x 128 tiles).
-template <int MODE, bool OUT_F32, int NRES, int OCC, bool TMAOUT>
+// TMAOUT: 0 = transposing epilogue; 1 = plain bf16 output through TMA stores; 2 = the derivative-saving activation epilogues
+// (GELU_G / QGELU_G) through TMA stores: activation -> `out` (tmC), derivative -> `out_pre` (tmC2), two staging tiles.
+template <int MODE, bool OUT_F32, int NRES, int OCC, int TMAOUT>
 __global__ void __launch_bounds__(64 + epi_warps(OCC) * 32, OCC == 3 ? 1 : OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmC, const Params p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for SWIZZLE_128B, by pointer arithmetic on the shared pointer (keeps ld/st.shared addressing)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -339,6 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instead of ~17 through the transposing epilogue below, which was issue-bound at K = 96 (ncu: 51 % issue
       // slots busy, 41 % DRAM throughput; profiles/r01e).  Row / column tails are clipped by the tensor map.
       uint8_t* stile = reinterpret_cast<uint8_t*>(staging);
+      uint8_t* stile2 = stile + ((p.BN + 63) >> 6) * kABytes;   // TMAOUT == 2: the derivative tile
       const int trow = q * 32 + lane;
       bool first = true;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -374,10 +387,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
             }
             const int cc = c0 + 8 * j;
+            const uint32_t soff = (uint32_t)((cc >> 6) * kABytes + trow * 128 + ((((cc & 63) >> 3) ^ (trow & 7)) << 4));
             Vec<bf16> pk;
+            if (TMAOUT == 2) {
+              Vec<bf16> dk;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pk.v[i] = o[i];
-            pk.store(reinterpret_cast<bf16*>(stile + (cc >> 6) * kABytes + trow * 128 + ((((cc & 63) >> 3) ^ (trow & 7)) << 4)));
+              for (int i = 0; i < 8; ++i) {
+                float y, d;
+                if (MODE == STGCMA_EPI_GELU_G) gelu_val_grad_act(o[i], y, d);
+                else qgelu_val_grad(o[i], y, d);
+                pk.v[i] = y;
+                dk.v[i] = d;
+              }
+              dk.store(reinterpret_cast<bf16*>(stile2 + soff));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk.v[i] = o[i];
+            }
+            pk.store(reinterpret_cast<bf16*>(stile + soff));
           }
         }
         tc_fence_before();
@@ -392,6 +419,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                          ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(stile + cb * kABytes)), "r"(n_blk * p.BN + cb * 64),
                            "r"(m_blk * BM), "r"(g)
                          : "memory");
+            if (TMAOUT == 2)
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(smem_u32(stile2 + cb * kABytes)), "r"(n_blk * p.BN + cb * 64),
+                             "r"(m_blk * BM), "r"(g)
+                           : "memory");
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -501,7 +533,15 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   // measured (scripts/gemm_shapes.py, 64 clips): fc1 + GELU' stage 2 3.50 -> 3.16 ms, its MULAUX backward 3.61 -> 3.13 ms, the
   // stage-3 pair 0.70 / 0.68 -> 0.66 / 0.61 ms; the plain wide-N GEMMs (qkv) lose 1 - 4 % to the shallower ring: not routed here
   if (epw16 && ep.mode != STGCMA_EPI_LINEAR && K >= 256 && K < 1024 && N >= 1024) occ = 3;
-  const int bn_max = occ != 2 ? 256 : 128;
+  // The derivative-saving activation epilogues of those shapes are ISSUE bound: 40 instructions per output element at 78 % of the
+  // issue slots (ncu, profiles/r02d_ncu_gemm_fc1g_s2.txt), ~30 of them the erf / expf / rcp evaluation -- hence the tanh form
+  // (gelu_val_grad_act: 3.15 -> 2.66 ms per step at stage 2).  Opt-in experiment (STGCMA_GEMM_ACT_TMA=1): lane-per-row into two
+  // swizzled staging tiles + two TMA stores with 128-wide tiles; fewer instructions (35 -> 19 per element) but measured SLOWER
+  // (3.20 ms: two block barriers per tile around the single-buffered staging tiles, twice the tiles), so it is off.
+  static const int act_tma = getenv("STGCMA_GEMM_ACT_TMA") ? atoi(getenv("STGCMA_GEMM_ACT_TMA")) : 0;
+  const bool tma_act = act_tma && occ == 3 && (ep.mode == STGCMA_EPI_GELU_G || ep.mode == STGCMA_EPI_QGELU_G) && ep.out_pre &&
+                       !ep.out_f32 && !ep.rowscale && N % 128 == 0;
+  const int bn_max = (occ != 2 && !tma_act) ? 256 : 128;
   int best_bn = 16;
   int64_t best_cost = -1;
   for (int bn = bn_max; bn >= 16; bn -= 16) {
@@ -536,7 +576,7 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   p.tmem_cols = cols;
   p.epi = ep;
 
-  CUtensorMap tmA, tmW, tmC;
+  CUtensorMap tmA, tmW, tmC, tmC2;
   int rc = make_map(&tmA, A, p.group_rows, K, lda, groups, BM);
   if (rc) return rc;
   rc = make_map(&tmW, W, N, K, ldw, groups, p.BN);
@@ -544,8 +584,13 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   // plain bf16 output -> TMA-store epilogue (needs the two-block staging tile: BN <= 128)
   const bool tma_out = tma_cand && p.BN <= 128 && (p.n_tiles == 1 || p.BN % 64 == 0);
   tmC = tmA;
-  if (tma_out) {
+  tmC2 = tmA;
+  if (tma_out || tma_act) {
     rc = make_map(&tmC, ep.out, p.group_rows, N, ep.ldo, groups, BM);
+    if (rc) return rc;
+  }
+  if (tma_act) {
+    rc = make_map(&tmC2, ep.out_pre, p.group_rows, N, ep.ldo, groups, BM);
     if (rc) return rc;
   }
 
@@ -559,9 +604,9 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
   }
 #define STG_TC_LAUNCH(MODE_, F32_, NRES_)                                                                      \
   do {                                                                                                         \
-    if (occ == 3) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 3, false);                                                \
-    if (occ == 1) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 1, false);                                                \
-    STG_TC_LAUNCH2(MODE_, F32_, NRES_, 2, false);                                                              \
+    if (occ == 3) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 3, 0);                                                    \
+    if (occ == 1) STG_TC_LAUNCH2(MODE_, F32_, NRES_, 1, 0);                                                    \
+    STG_TC_LAUNCH2(MODE_, F32_, NRES_, 2, 0);                                                                  \
   } while (0)
 #define STG_TC_LAUNCH2(MODE_, F32_, NRES_, OCC_, TMA_)                                                         \
   do {                                                                                                         \
@@ -573,13 +618,17 @@ static int launch(const void* A, const void* W, int64_t M, int N, int K, int64_t
       set_error("gemm: cannot raise dynamic smem limit: %s", cudaGetErrorString(attr_err));                    \
       return STGCMA_ECUDA;                                                                                     \
     }                                                                                                          \
-    kern<<<grid, kThreads, smem, st>>>(tmA, tmW, tmC, p);                                                         \
+    kern<<<grid, kThreads, smem, st>>>(tmA, tmW, tmC, tmC2, p);                                                   \
     return check_launch("gemm(tcgen05)");                                                                      \
   } while (0)
   const bool f32 = ep.out_f32 != 0;
   if (tma_out) {
-    if (occ == 1) STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 1, true);
-    if (occ == 2) STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 2, true);
+    if (occ == 1) STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 1, 1);
+    if (occ == 2) STG_TC_LAUNCH2(STGCMA_EPI_LINEAR, false, 0, 2, 1);
+  }
+  if (tma_act) {
+    if (ep.mode == STGCMA_EPI_GELU_G) STG_TC_LAUNCH2(STGCMA_EPI_GELU_G, false, 0, 3, 2);
+    STG_TC_LAUNCH2(STGCMA_EPI_QGELU_G, false, 0, 3, 2);
   }
   switch (ep.mode) {
     case STGCMA_EPI_LINEAR:
