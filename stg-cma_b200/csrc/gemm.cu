@@ -154,8 +154,9 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int64_t off, int p
     float t[8];
     unpack8(r.a[ps][0], t);
 #pragma unroll
-    // (the MUFU-free polynomials of gelu_poly.cuh are ~25 % cheaper here but moved one stage-2 temporal-bias-table
-    //  gradient of the T = 2 golden fixture from 1.9e-2 to 2.4e-2 relative L2: the erf forms stay)
+    // (round 1 kept the erf forms here because the polynomial forms "moved one temporal-bias-table gradient from 1.9e-2 to
+    //  2.4e-2"; the round-2 noise analysis -- DESIGN.md section 4 -- shows that was a re-draw of the bf16 storage noise, not an
+    //  accuracy loss.  These dX epilogues have N = rp <= 96 columns and are not the bottleneck of their GEMMs, so they stay.)
     for (int i = 0; i < 8; ++i)
       v[i] *= (MODE == STGCMA_EPI_DGELU) ? gelu_grad_fast(t[i]) : (MODE == STGCMA_EPI_DQGELU) ? qgelu_grad(t[i]) : t[i];
   }
